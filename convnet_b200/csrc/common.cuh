@@ -1,0 +1,74 @@
+// common.cuh — library-wide state and helpers (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+
+#include "../../include/cudamat_abi.h"
+
+namespace cnb {
+
+// ---- error handling: same contract as the reference (cudamat_conv_gemm.cu:35-42):
+// CUDA errors print and exit(EXIT_FAILURE); shape errors print and abort().
+#define CNB_CUDA_CHECK(expr)                                                              \
+  do {                                                                                    \
+    cudaError_t _e = (expr);                                                              \
+    if (_e != cudaSuccess) {                                                              \
+      fprintf(stderr, "%s(%d) : convnet_b200 CUDA error : %s : (%d) %s.\n", __FILE__,     \
+              __LINE__, #expr, (int)_e, cudaGetErrorString(_e));                          \
+      exit(EXIT_FAILURE);                                                                 \
+    }                                                                                     \
+  } while (0)
+
+#define CNB_LAUNCH_CHECK(what)                                                            \
+  do {                                                                                    \
+    cudaError_t _e = cudaGetLastError();                                                  \
+    if (_e != cudaSuccess) {                                                              \
+      fprintf(stderr, "%s(%d) : getLastCudaError() CUDA error : %s : (%d) %s.\n",         \
+              __FILE__, __LINE__, what, (int)_e, cudaGetErrorString(_e));                 \
+      exit(EXIT_FAILURE);                                                                 \
+    }                                                                                     \
+  } while (0)
+
+#define CNB_REQUIRE(cond, what)                                                           \
+  do {                                                                                    \
+    if (!(cond)) {                                                                        \
+      fprintf(stderr, "convnet_b200: %s: requirement failed: %s (%s:%d)\n", what, #cond,  \
+              __FILE__, __LINE__);                                                        \
+      abort();                                                                            \
+    }                                                                                     \
+  } while (0)
+
+[[noreturn]] inline void not_implemented(const char* sym, const char* why) {
+  fprintf(stderr, "convnet_b200: %s is not implemented: %s\n", sym, why);
+  abort();
+}
+
+// ---- global state (one host thread per process/GPU, like the reference) -------------
+enum Precision { kPrecFP32 = 0, kPrecTF32 = 1, kPrecBF16 = 2 };
+enum ConvPath { kPathNone = -1, kPathSimt = 0, kPathTcTf32 = 1, kPathTcBf16 = 2 };
+
+struct State {
+  cudaStream_t stream = 0;          // legacy default stream, like every reference kernel
+  int precision = kPrecTF32;
+  int last_conv_path = kPathNone;
+  unsigned long long launches = 0;  // kernels launched by this library
+  // scratch (wgrad partial sums, rnorm-free) — grown on demand, never per-call malloc'd
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  int ws_device = -1;
+  int num_sms = 0;
+  int sm_device = -1;
+};
+State& state();
+
+void* workspace(size_t bytes);       // device scratch of at least `bytes`, valid until next call
+int num_sms();
+
+inline void count_launch(int n = 1) { state().launches += n; }
+
+template <typename T>
+__host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }
+
+}  // namespace cnb

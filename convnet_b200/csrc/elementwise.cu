@@ -1,0 +1,131 @@
+// elementwise.cu — the memory-bound steps the Edge layer runs either side of the conv ops
+// (bias add, bias gradient, ReLU, SGD).  See include/convnet_b200_ext.h for the reference
+// call sites they correspond to.  All are single-pass, float4-vectorised where aligned.
+#include <algorithm>
+
+#include "../../include/convnet_b200_ext.h"
+#include "common.cuh"
+
+namespace cnb {
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static int blocks_for(long long work, int threads) {
+  return (int)std::max<long long>(1, std::min<long long>(ceil_div<long long>(work, threads), (long long)num_sms() * 16));
+}
+
+template <bool RELU>
+__global__ void bias_kernel(float* acts, const float* __restrict__ bias, long long rows, int cols) {
+  // rows % 4 == 0 guaranteed by caller for the vector path
+  const long long rv = rows / 4, total = rv * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const float b = __ldg(bias + i / rv);
+    float4 v = reinterpret_cast<float4*>(acts)[i];
+    v.x += b; v.y += b; v.z += b; v.w += b;
+    if (RELU) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+    reinterpret_cast<float4*>(acts)[i] = v;
+  }
+}
+template <bool RELU>
+__global__ void bias_kernel_scalar(float* acts, const float* __restrict__ bias, long long rows, int cols) {
+  const long long total = rows * cols;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    float v = acts[i] + __ldg(bias + i / rows);
+    acts[i] = RELU ? fmaxf(v, 0.f) : v;
+  }
+}
+
+template <bool RELU>
+static void bias_launch(float* acts, const float* bias, long long rows, int cols) {
+  if (rows <= 0 || cols <= 0) return;
+  if (rows % 4 == 0 && aligned16(acts)) {
+    bias_kernel<RELU><<<blocks_for(rows / 4 * cols, 256), 256, 0, state().stream>>>(acts, bias, rows, cols);
+  } else {
+    bias_kernel_scalar<RELU><<<blocks_for(rows * cols, 256), 256, 0, state().stream>>>(acts, bias, rows, cols);
+  }
+  count_launch();
+  CNB_LAUNCH_CHECK("add_channel_bias");
+}
+
+// column sums of a column-major [rows x cols] matrix; one block per (column, row-slice)
+__global__ void colsum_partial_kernel(const float* __restrict__ a, float* __restrict__ part, long long rows, int cols,
+                                      int slices) {
+  const int col = blockIdx.x, slice = blockIdx.y;
+  const long long per = ceil_div<long long>(rows, slices);
+  const long long r0 = slice * per, r1 = min(rows, r0 + per);
+  const float* p = a + (long long)col * rows;
+  float s = 0.f;
+  for (long long r = r0 + threadIdx.x; r < r1; r += blockDim.x) s += __ldg(p + r);
+  __shared__ float sh[32];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) part[(long long)slice * cols + col] = s;
+  }
+}
+__global__ void colsum_final_kernel(const float* __restrict__ part, float* out, int cols, int slices, float st, float so) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  float s = 0.f;
+  for (int j = 0; j < slices; j++) s += part[(long long)j * cols + c];
+  out[c] = (st == 0.f) ? so * s : st * out[c] + so * s;
+}
+
+__global__ void relu_kernel(float* x, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    x[i] = fmaxf(x[i], 0.f);
+}
+__global__ void relu_deriv_kernel(float* dx, const float* __restrict__ y, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    dx[i] = y[i] > 0.f ? dx[i] : 0.f;
+}
+__global__ void sgd_kernel(float* w, float* h, const float* __restrict__ g, long long n, float lr, float mom, float l2) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float wi = w[i];
+    const float hi = mom * h[i] + lr * (g[i] + l2 * wi);
+    h[i] = hi;
+    w[i] = wi - hi;
+  }
+}
+
+}  // namespace cnb
+
+using namespace cnb;
+
+extern "C" {
+
+void cnb_add_channel_bias(float* acts, const float* bias, long long rows, int cols) {
+  bias_launch<false>(acts, bias, rows, cols);
+}
+void cnb_add_channel_bias_relu(float* acts, const float* bias, long long rows, int cols) {
+  bias_launch<true>(acts, bias, rows, cols);
+}
+void cnb_channel_bias_grad(const float* derivs, float* grad_bias, long long rows, int cols, float st, float so) {
+  if (cols <= 0) return;
+  int slices = (int)std::max<long long>(1, std::min<long long>(64, (4LL * num_sms()) / cols));
+  slices = (int)std::min<long long>(slices, std::max<long long>(1, rows / 1024));
+  float* part = (float*)workspace(sizeof(float) * (size_t)slices * cols);
+  colsum_partial_kernel<<<dim3(cols, slices), 256, 0, state().stream>>>(derivs, part, rows, cols, slices);
+  colsum_final_kernel<<<ceil_div(cols, 128), 128, 0, state().stream>>>(part, grad_bias, cols, slices, st, so);
+  count_launch(2);
+  CNB_LAUNCH_CHECK("channel_bias_grad");
+}
+void cnb_relu(float* x, long long n) {
+  if (n <= 0) return;
+  relu_kernel<<<blocks_for(n, 256), 256, 0, state().stream>>>(x, n);
+  count_launch(); CNB_LAUNCH_CHECK("relu");
+}
+void cnb_relu_deriv(float* dx, const float* y, long long n) {
+  if (n <= 0) return;
+  relu_deriv_kernel<<<blocks_for(n, 256), 256, 0, state().stream>>>(dx, y, n);
+  count_launch(); CNB_LAUNCH_CHECK("relu_deriv");
+}
+void cnb_sgd_momentum(float* w, float* hist, const float* grad, long long n, float lr, float momentum, float l2) {
+  if (n <= 0) return;
+  sgd_kernel<<<blocks_for(n, 256), 256, 0, state().stream>>>(w, hist, grad, n, lr, momentum, l2);
+  count_launch(); CNB_LAUNCH_CHECK("sgd_momentum");
+}
+
+}  // extern "C"

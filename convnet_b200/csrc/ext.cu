@@ -1,0 +1,87 @@
+// ext.cu — library state, scratch, and the extension C API (include/convnet_b200_ext.h).
+#include <string.h>
+
+#include "../../include/convnet_b200_ext.h"
+#include "common.cuh"
+
+namespace cnb {
+
+State& state() {
+  static State s;
+  static bool init = false;
+  if (!init) {
+    init = true;
+    const char* e = getenv("CONVNET_B200_PRECISION");
+    if (e) {
+      if (!strcmp(e, "fp32")) s.precision = kPrecFP32;
+      else if (!strcmp(e, "tf32")) s.precision = kPrecTF32;
+      else if (!strcmp(e, "bf16")) s.precision = kPrecBF16;
+      else { fprintf(stderr, "convnet_b200: unknown CONVNET_B200_PRECISION '%s'\n", e); abort(); }
+    }
+  }
+  return s;
+}
+
+void* workspace(size_t bytes) {
+  State& s = state();
+  int dev = 0;
+  CNB_CUDA_CHECK(cudaGetDevice(&dev));
+  if (s.ws && (s.ws_device != dev || s.ws_bytes < bytes)) {
+    // growing: wait for users of the old block on our stream, then free
+    CNB_CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    int cur = dev;
+    if (s.ws_device != dev) CNB_CUDA_CHECK(cudaSetDevice(s.ws_device));
+    CNB_CUDA_CHECK(cudaFree(s.ws));
+    if (s.ws_device != cur) CNB_CUDA_CHECK(cudaSetDevice(cur));
+    s.ws = nullptr; s.ws_bytes = 0;
+  }
+  if (!s.ws) {
+    size_t want = bytes < (size_t(64) << 20) ? (size_t(64) << 20) : bytes;
+    cudaError_t e = cudaMalloc(&s.ws, want);
+    if (e != cudaSuccess) {
+      fprintf(stderr, "convnet_b200: could not allocate %zu bytes of scratch: %s\n", want, cudaGetErrorString(e));
+      exit(EXIT_FAILURE);
+    }
+    s.ws_bytes = want; s.ws_device = dev;
+  }
+  return s.ws;
+}
+
+int num_sms() {
+  State& s = state();
+  int dev = 0;
+  CNB_CUDA_CHECK(cudaGetDevice(&dev));
+  if (s.sm_device != dev) {
+    CNB_CUDA_CHECK(cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev));
+    s.sm_device = dev;
+  }
+  return s.num_sms;
+}
+
+}  // namespace cnb
+
+using namespace cnb;
+
+extern "C" {
+
+int convnet_b200_version(void) { return 100; }
+void convnet_b200_set_stream(void* cuda_stream) { state().stream = (cudaStream_t)cuda_stream; }
+void* convnet_b200_get_stream(void) { return (void*)state().stream; }
+void convnet_b200_set_conv_precision(int mode) {
+  CNB_REQUIRE(mode >= 0 && mode <= 2, "convnet_b200_set_conv_precision");
+  state().precision = mode;
+}
+int convnet_b200_get_conv_precision(void) { return state().precision; }
+int convnet_b200_last_conv_path(void) { return state().last_conv_path; }
+unsigned long long convnet_b200_launch_count(void) { return state().launches; }
+void convnet_b200_reset_launch_count(void) { state().launches = 0; }
+void convnet_b200_release_workspace(void) {
+  State& s = state();
+  if (s.ws) {
+    CNB_CUDA_CHECK(cudaStreamSynchronize(s.stream));
+    CNB_CUDA_CHECK(cudaFree(s.ws));
+    s.ws = nullptr; s.ws_bytes = 0; s.ws_device = -1;
+  }
+}
+
+}  // extern "C"

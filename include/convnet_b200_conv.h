@@ -15,6 +15,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
 
 /* cudamat_conv_util.cu (texture-object cache): nothing to set up on sm_100a; no-op. */
 void SetupTexture(cudamat* mat);
@@ -91,6 +94,9 @@ void DownSample(cudamat* images, cudamat* targets, Shape4D* images_shape,
 /* cudamat_conv_others.cu:3757: out of scope (RGBToYUVEdge uses a 3x3 dot); abort()s. */
 void RGBToYUV(cudamat* images, cudamat* targets);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

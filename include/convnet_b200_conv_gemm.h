@@ -23,6 +23,9 @@
 #ifdef __cplusplus
 extern "C" {
 #endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
 
 /* fprop.  targets = scaleTargets*targets + conv(images, filters).
  * replaces cudamat_conv_gemm.cu:1411 (-> _convUpGemm :545-682).
@@ -151,6 +154,9 @@ void ResponseNormCrossMap3DUndoGemm(cudamat* outGrads, cudamat* inputs,
                                     float addScale, float powScale, bool blocked,
                                     int image_size_t);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

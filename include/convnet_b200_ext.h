@@ -1,0 +1,76 @@
+/* convnet_b200_ext.h — additions to the reference's C surface (everything here is
+ * new; nothing replaces a reference symbol).  Plain C ABI: pointers and scalars only.
+ */
+#ifndef CONVNET_B200_EXT_H_
+#define CONVNET_B200_EXT_H_
+
+#include "cudamat_abi.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)   /* the library is built with -fvisibility=hidden */
+#endif
+
+/* Library version (major*10000 + minor*100 + patch). */
+int convnet_b200_version(void);
+
+/* Stream every kernel of this library is enqueued on.  Default: the legacy
+ * default stream 0, which is what every reference kernel uses
+ * (cudamat_conv_filteracts.cu:1259), so ordering against libcudamat.so is kept.
+ * `cuda_stream` is a cudaStream_t / CUstream handle. */
+void convnet_b200_set_stream(void* cuda_stream);
+void* convnet_b200_get_stream(void);
+
+/* Arithmetic of the three conv ops (pool / response-norm are always fp32):
+ *   0  FP32  fp32 FMA on CUDA cores; meets the reference's own 1e-4 kernel test
+ *            tolerance (py/test_conv.py:387) and is what run_grad_check should use
+ *   1  TF32  tcgen05 kind::tf32 on the caller's fp32 buffers, fp32 accumulate (default);
+ *            Diff <= 2e-3
+ *   2  BF16  tcgen05 kind::f16 on bf16 copies, fp32 accumulate; Diff <= 2e-2
+ * Shapes the tensor-core path does not take fall through to FP32.  Also settable
+ * with CONVNET_B200_PRECISION={fp32,tf32,bf16} before first use. */
+void convnet_b200_set_conv_precision(int mode);
+int convnet_b200_get_conv_precision(void);
+
+/* Which path the most recent conv call took: 0 CUDA-core fp32, 1 tcgen05 tf32,
+ * 2 tcgen05 bf16, -1 none yet.  (tests assert the tensor path really ran) */
+int convnet_b200_last_conv_path(void);
+
+/* Number of kernels this library has launched since the last reset. */
+unsigned long long convnet_b200_launch_count(void);
+void convnet_b200_reset_launch_count(void);
+
+/* Free cached device scratch (wgrad partial sums).  Never required. */
+void convnet_b200_release_workspace(void);
+
+/* ---- steps either side of the conv ops that the Edge layer sequences ------------
+ * (in the reference these are libcudamat.so calls:
+ *  add_row_vec cudamat.cu:1064, sum_by_axis :1614, lower_bound_scalar :1426,
+ *  apply_rectified_linear_deriv :2475).  Names are prefixed so both libraries link. */
+
+/* acts (N, locs, C): acts[n, l, c] += bias[c]  — ConvEdge::ComputeUp shared bias,
+ * src/conv_edge.cc:143-152.  rows = N*locs, cols = C. */
+void cnb_add_channel_bias(float* acts, const float* bias, long long rows, int cols);
+/* same, fused with ReLU (Layer::ApplyActivation, src/layer.cc:550: LowerBound(0)). */
+void cnb_add_channel_bias_relu(float* acts, const float* bias, long long rows, int cols);
+/* grad_bias[c] = scaleTargets*grad_bias[c] + scaleOutput * sum_{rows} derivs[r, c]
+ * — src/conv_edge.cc:210-222 (two-step SumRows). Deterministic. */
+void cnb_channel_bias_grad(const float* derivs, float* grad_bias, long long rows, int cols,
+                           float scaleTargets, float scaleOutput);
+/* x = max(x, 0) ; dx *= (y > 0) */
+void cnb_relu(float* x, long long n);
+void cnb_relu_deriv(float* dx, const float* y, long long n);
+/* SGD with momentum and L2 decay, one fused pass (src/optimizer.cc:174-200):
+ *   g' = lr*(g + l2*w);  h = momentum*h + g';  w -= h */
+void cnb_sgd_momentum(float* w, float* hist, const float* grad, long long n, float lr,
+                      float momentum, float l2);
+
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
+#ifdef __cplusplus
+}
+#endif
+#endif  /* CONVNET_B200_EXT_H_ */
