@@ -1,7 +1,580 @@
-// conv_tc.cu — tcgen05 / TMA implicit-GEMM convolution (placeholder until the kernel lands).
+// conv_tc.cu — convolution fprop / dgrad / wgrad as implicit GEMMs on the 5th-generation
+// tensor cores (tcgen05.mma, accumulators in TMEM) fed by TMA straight from the caller's
+// fp32 CHWN buffers.  No im2col buffer, no layout conversion pass, no atomics.
+//
+// Layout insight: in the reference layout the IMAGE index n is the
+// contiguous axis of every activation tensor.  A box of 32
+// consecutive images x 32 channels at one pixel is therefore a ready-made MN-major
+// SWIZZLE_128B UMMA operand atom stack (32 rows of 128 bytes), and zero-fill of
+// out-of-range TMA coordinates implements the convolution padding for free.  Filters
+// [K x Cout] (Cout contiguous) are MN-major B for fprop and K-major B for dgrad.
+//
+//   fprop : D[(n,module), o] = sum_{tap,c}  img[n, x(module,tap), y, c] * w[o, tap, c]     A MN-major, B MN-major
+//   dgrad : D[(n,pixel), c]  = sum_{tap,o}  der[n, module(pixel,tap), o] * w[o, tap, c]    A MN-major, B K-major
+//   wgrad : D[o, c] (per tap)= sum_{module,n} der[n, module, o] * img[n, x, y, c]          A K-major,  B K-major
+//
+// One persistent CTA per SM, 6 warps: warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM
+// allocator), warps 2..5 = epilogue (TMEM -> registers -> coalesced global stores; each thread
+// owns one image / one output channel row, so every store instruction writes 128 contiguous bytes).
+// Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
+#include <algorithm>
+
 #include "conv_kernels.h"
+#include "sm100_ptx.cuh"
+
 namespace cnb {
-bool tc_conv_up(const ConvGeom&, const float*, const float*, float*, float, float) { return false; }
-bool tc_conv_down(const ConvGeom&, const float*, const float*, float*, float, float) { return false; }
-bool tc_conv_outp(const ConvGeom&, const float*, const float*, float*, float, float) { return false; }
+
+namespace {
+
+constexpr int kThreads = 192;
+constexpr int BM = 128;             // GEMM rows per tile  (4 chunks of 32)
+constexpr int BK = 32;              // fp32 elements of K per pipeline stage (4 UMMA steps of 8)
+constexpr int kMaxStages = 8;
+constexpr uint32_t kAStageBytes = BM * BK * 4;   // 16 KiB
+
+enum Op { kFprop = 0, kDgrad = 1, kWgrad = 2 };
+
+struct TcParams {
+  int N, nb;                        // images, ceil(N/32)
+  int W, H, modX, modY, modules;
+  int Cin, Cout;                    // channel sub-range sizes
+  int kx, ky, sx, sy, px, py, taps;
+  int frames, frame0;               // fprop/wgrad: number of frames; dgrad: the single frame handled by this launch
+  int BN, stages, tmem_cols;
+  int m_tiles, n_tiles, num_tiles;
+  int kc_blocks;                    // ceil(K-side channels / 32)
+  long long total_chunks;           // fprop: nb*modules*frames ; dgrad: nb*W*H
+  int splits, units_per_split;      // wgrad: (frame,module) units per reduction split
+  float* out;
+  float st, so;
+  long long out_frame_step;         // fprop: floats between output frames
+  uint32_t idesc;
+};
+
+struct __align__(8) SmemCtl {
+  uint64_t full[kMaxStages];
+  uint64_t empty[kMaxStages];
+  uint64_t tmem_full[2];
+  uint64_t tmem_empty[2];
+  uint32_t tmem_base;
+};
+
+// ------------------------------------------------------------------------------------------------
+// k-block enumeration, shared by the producer (which loads) and the MMA warp (which only counts)
+// ------------------------------------------------------------------------------------------------
+// dgrad: module coordinate touched by tap t at input coordinate X, or -1
+__device__ __forceinline__ int dgrad_mod(int X, int p, int t, int s, int mods) {
+  const int a = X - p - t;
+  if (a < 0) return -1;
+  const int m = a / s;
+  if (m * s != a || m >= mods) return -1;
+  return m;
 }
+
+template <int OP>
+struct Tile {
+  int m_tile, n_tile;               // fprop/dgrad
+  int tap, o_tile, c_tile, split;   // wgrad
+};
+
+template <int OP>
+__device__ __forceinline__ Tile<OP> decode_tile(const TcParams& p, int t) {
+  Tile<OP> r;
+  if (OP == kWgrad) {
+    r.split = t % p.splits; t /= p.splits;
+    r.c_tile = t % p.n_tiles; t /= p.n_tiles;
+    r.o_tile = t % p.m_tiles; t /= p.m_tiles;
+    r.tap = t;
+    r.m_tile = r.o_tile; r.n_tile = r.c_tile;
+  } else {
+    r.n_tile = t % p.n_tiles;
+    r.m_tile = t / p.n_tiles;
+    r.tap = r.o_tile = r.c_tile = r.split = 0;
+  }
+  return r;
+}
+
+// fprop / dgrad chunk -> (image block, position, frame)
+__device__ __forceinline__ void decode_chunk(const TcParams& p, long long q, int per_frame, int& ib, int& pos, int& f) {
+  ib = (int)(q % p.nb);
+  const long long r = q / p.nb;
+  pos = (int)(r % per_frame);
+  f = (int)(r / per_frame);
+}
+
+// dgrad: is tap (tx,ty) live for ANY chunk of this m-tile?
+__device__ __forceinline__ bool dgrad_tap_live(const TcParams& p, int m_tile, int tx, int ty) {
+#pragma unroll
+  for (int c = 0; c < 4; c++) {
+    const long long q = (long long)m_tile * 4 + c;
+    if (q >= p.total_chunks) continue;
+    int ib, pix, f;
+    decode_chunk(p, q, p.W * p.H, ib, pix, f);
+    if (dgrad_mod(pix % p.W, p.px, tx, p.sx, p.modX) >= 0 && dgrad_mod(pix / p.W, p.py, ty, p.sy, p.modY) >= 0)
+      return true;
+  }
+  return false;
+}
+
+// wgrad: does tap (tx,ty) of module (mx,my) fall inside the image?
+__device__ __forceinline__ bool wgrad_unit_live(const TcParams& p, int mod, int tx, int ty) {
+  const int X = (mod % p.modX) * p.sx + p.px + tx, Y = (mod / p.modX) * p.sy + p.py + ty;
+  return (unsigned)X < (unsigned)p.W && (unsigned)Y < (unsigned)p.H;
+}
+
+template <int OP>
+__device__ __forceinline__ int count_kblocks(const TcParams& p, const Tile<OP>& t) {
+  if (OP == kFprop) return p.taps * p.kc_blocks;
+  if (OP == kDgrad) {
+    int live = 0;
+    for (int tap = 0; tap < p.taps; tap++) live += dgrad_tap_live(p, t.m_tile, tap % p.kx, tap / p.kx) ? 1 : 0;
+    return max(live, 1) * p.kc_blocks;
+  }
+  // wgrad
+  const int u0 = t.split * p.units_per_split, u1 = min(u0 + p.units_per_split, p.modules * p.frames);
+  int live = 0;
+  for (int u = u0; u < u1; u++) live += wgrad_unit_live(p, u % p.modules, t.tap % p.kx, t.tap / p.kx) ? 1 : 0;
+  return max(live, 1) * p.nb;
+}
+
+// ------------------------------------------------------------------------------------------------
+template <int OP>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const uint32_t b_stage_bytes = (uint32_t)p.BN * BK * 4;
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + (size_t)p.stages * kAStageBytes;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smemB + (size_t)p.stages * b_stage_bytes);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; s++) { ptx::mbar_init(&ctl->full[s], 1); ptx::mbar_init(&ctl->empty[s], 1); }
+    for (int a = 0; a < 2; a++) { ptx::mbar_init(&ctl->tmem_full[a], 1); ptx::mbar_init(&ctl->tmem_empty[a], 4); }
+    ptx::fence_barrier_init();
+    ptx::tma_prefetch_desc(&mapA);
+    ptx::tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) { ptx::tmem_alloc(&ctl->tmem_base, (uint32_t)p.tmem_cols); ptx::tmem_relinquish(); }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = ctl->tmem_base;
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      const uint32_t tx_bytes = kAStageBytes + b_stage_bytes;
+      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+        const Tile<OP> tile = decode_tile<OP>(p, t);
+        auto begin_stage = [&]() -> uint8_t* {
+          ptx::mbar_wait(&ctl->empty[stage], phase ^ 1);
+          ptx::mbar_arrive_expect_tx(&ctl->full[stage], tx_bytes);
+          return smemA + (size_t)stage * kAStageBytes;
+        };
+        auto end_stage = [&]() { if (++stage == p.stages) { stage = 0; phase ^= 1; } };
+
+        if (OP == kFprop) {
+          // chunk coordinates of this m-tile
+          int cn[4], cX[4], cY[4], cF[4];
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const long long q = (long long)tile.m_tile * 4 + c;
+            if (q < p.total_chunks) {
+              int ib, mod, f; decode_chunk(p, q, p.modules, ib, mod, f);
+              cn[c] = ib * 32; cX[c] = (mod % p.modX) * p.sx + p.px; cY[c] = (mod / p.modX) * p.sy + p.py; cF[c] = f;
+            } else { cn[c] = p.N; cX[c] = 0; cY[c] = 0; cF[c] = 0; }    // n >= N: whole box zero-filled
+          }
+          for (int tap = 0; tap < p.taps; tap++) {
+            const int tx = tap % p.kx, ty = tap / p.kx;
+            for (int cb = 0; cb < p.kc_blocks; cb++) {
+              uint8_t* a = begin_stage();
+              uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
+#pragma unroll
+              for (int c = 0; c < 4; c++)
+                ptx::tma_load_5d(&mapA, &ctl->full[stage], a + c * (BK * 128), cn[c], cb * BK, cX[c] + tx, cY[c] + ty, cF[c]);
+              for (int j = 0; j < p.BN / 32; j++)
+                ptx::tma_load_3d(&mapB, &ctl->full[stage], b + j * (BK * 128), tile.n_tile * p.BN + j * 32, tap, cb * BK);
+              end_stage();
+            }
+          }
+        } else if (OP == kDgrad) {
+          int cn[4], cX[4], cY[4];
+#pragma unroll
+          for (int c = 0; c < 4; c++) {
+            const long long q = (long long)tile.m_tile * 4 + c;
+            if (q < p.total_chunks) {
+              int ib, pix, f; decode_chunk(p, q, p.W * p.H, ib, pix, f);
+              cn[c] = ib * 32; cX[c] = pix % p.W; cY[c] = pix / p.W;
+            } else { cn[c] = p.N; cX[c] = -1000000; cY[c] = -1000000; }
+          }
+          bool any = false;
+          for (int tap = 0; tap < p.taps; tap++) {
+            const int tx = tap % p.kx, ty = tap / p.kx;
+            bool live = dgrad_tap_live(p, tile.m_tile, tx, ty);
+            if (!live && !(tap == p.taps - 1 && !any)) continue;   // keep >= 1 k-block per tile (all-zero operands)
+            any = true;
+            int mx[4], my[4];
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+              mx[c] = dgrad_mod(cX[c], p.px, tx, p.sx, p.modX);
+              my[c] = dgrad_mod(cY[c], p.py, ty, p.sy, p.modY);
+              if (mx[c] < 0 || my[c] < 0 || !live) { mx[c] = -1; my[c] = -1; }      // out of range -> zeros
+            }
+            for (int ob = 0; ob < p.kc_blocks; ob++) {
+              uint8_t* a = begin_stage();
+              uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
+#pragma unroll
+              for (int c = 0; c < 4; c++)
+                ptx::tma_load_5d(&mapA, &ctl->full[stage], a + c * (BK * 128), cn[c], ob * BK, mx[c], my[c], p.frame0);
+              ptx::tma_load_3d(&mapB, &ctl->full[stage], b, ob * BK, tap, tile.n_tile * p.BN);
+              end_stage();
+            }
+          }
+        } else {
+          const int tx = tile.tap % p.kx, ty = tile.tap / p.kx;
+          const int u0 = tile.split * p.units_per_split, u1 = min(u0 + p.units_per_split, p.modules * p.frames);
+          bool any = false;
+          for (int u = u0; u < u1; u++) {
+            const int mod = u % p.modules, f = u / p.modules;
+            const bool live = wgrad_unit_live(p, mod, tx, ty);
+            if (!live && !(u == u1 - 1 && !any)) continue;
+            any = true;
+            const int mx = mod % p.modX, my = mod / p.modX;
+            const int X = mx * p.sx + p.px + tx, Y = my * p.sy + p.py + ty;     // dead unit: X/Y out of range -> zeros
+            for (int ib = 0; ib < p.nb; ib++) {
+              uint8_t* a = begin_stage();
+              uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
+              ptx::tma_load_5d(&mapA, &ctl->full[stage], a, ib * 32, mx, my, tile.o_tile * BM, f);
+              ptx::tma_load_5d(&mapB, &ctl->full[stage], b, ib * 32, X, Y, tile.c_tile * p.BN, f);
+              end_stage();
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer =================================
+    int stage = 0; uint32_t phase = 0;
+    int acc = 0; uint32_t acc_phase = 0;
+    // operand descriptors: MN-major tiles are [chunk][BK rows][128 B] (LBO = chunk stride, K step = 8 rows = 1 KiB);
+    // K-major tiles are [row][128 B] (SBO = 8 rows = 1 KiB, K step = 32 B inside the swizzle atom)
+    const bool a_mn = (OP != kWgrad), b_mn = (OP == kFprop);
+    const uint32_t a_lbo = a_mn ? BK * 128 : 16, b_lbo = b_mn ? BK * 128 : 16;
+    const uint32_t a_kstep = a_mn ? 1024 : 32, b_kstep = b_mn ? 1024 : 32;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const Tile<OP> tile = decode_tile<OP>(p, t);
+      const int nkb = count_kblocks<OP>(p, tile);
+      ptx::mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
+      for (int kb = 0; kb < nkb; kb++) {
+        ptx::mbar_wait(&ctl->full[stage], phase);
+        ptx::tc_fence_after();
+        if (lane == 0) {
+          const uint32_t a_addr = ptx::smem_u32(smemA + (size_t)stage * kAStageBytes);
+          const uint32_t b_addr = ptx::smem_u32(smemB + (size_t)stage * b_stage_bytes);
+#pragma unroll
+          for (int ks = 0; ks < BK / 8; ks++) {
+            const uint64_t da = ptx::make_smem_desc_sw128(a_addr + ks * a_kstep, a_lbo, 1024);
+            const uint64_t db = ptx::make_smem_desc_sw128(b_addr + ks * b_kstep, b_lbo, 1024);
+            ptx::mma_tf32(d_tmem, da, db, p.idesc, (kb | ks) != 0);
+          }
+          ptx::mma_commit(&ctl->empty[stage]);              // frees the smem slot when these MMAs retire
+          if (kb == nkb - 1) ptx::mma_commit(&ctl->tmem_full[acc]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  } else {
+    // =============================== epilogue ===================================
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
+      const Tile<OP> tile = decode_tile<OP>(p, t);
+      // row owned by this thread and the address of its column 0
+      float* row_ptr = nullptr;
+      long long col_stride = 0;
+      int ncols_valid = 0;
+      bool direct_scale = true;
+      if (OP == kFprop || OP == kDgrad) {
+        const long long q = (long long)tile.m_tile * 4 + quarter;
+        const int per_frame = (OP == kFprop) ? p.modules : p.W * p.H;
+        if (q < p.total_chunks) {
+          int ib, pos, f; decode_chunk(p, q, per_frame, ib, pos, f);
+          const int n = ib * 32 + lane;
+          if (n < p.N) {
+            col_stride = (long long)p.N * per_frame;
+            row_ptr = p.out + (OP == kFprop ? f * p.out_frame_step : 0) + n + (long long)p.N * pos +
+                      col_stride * ((long long)tile.n_tile * p.BN);
+          }
+        }
+        ncols_valid = min(p.BN, (OP == kFprop ? p.Cout : p.Cin) - tile.n_tile * p.BN);
+      } else {
+        const int o = tile.o_tile * BM + quarter * 32 + lane;
+        const int c0 = tile.c_tile * p.BN;
+        col_stride = (long long)p.Cout * p.taps;
+        if (o < p.Cout)
+          row_ptr = p.out + (long long)tile.split * p.Cout * p.taps * p.Cin + o + (long long)p.Cout * tile.tap + col_stride * c0;
+        ncols_valid = min(p.BN, p.Cin - c0);
+        direct_scale = (p.splits == 1);
+      }
+      ptx::mbar_wait(&ctl->tmem_full[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
+      for (int j0 = 0; j0 < p.BN; j0 += 32) {
+        float v[32];
+        ptx::tmem_ld_32x32(t_addr + j0, v);
+        ptx::tmem_ld_wait();
+        if (row_ptr != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            if (j0 + j < ncols_valid) {
+              float* dst = row_ptr + col_stride * (j0 + j);
+              float r = v[j];
+              if (direct_scale) r = (p.st == 0.f) ? p.so * r : p.st * (*dst) + p.so * r;
+              *dst = r;
+            }
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[acc]);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side
+// ------------------------------------------------------------------------------------------------
+PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
+  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    CNB_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
+    CNB_REQUIRE(qres == cudaDriverEntryPointSuccess && ptr != nullptr, "cuTensorMapEncodeTiled");
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
+  }
+  return fn;
+}
+
+// fp32 tensor map; dims[0] is the contiguous axis; strides in ELEMENTS for dims 1..rank-1
+bool make_map(CUtensorMap* map, const float* base, int rank, const long long* dims, const long long* strides,
+              const int* box) {
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bdim[5], estr[5];
+  if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
+  for (int i = 0; i < rank; i++) {
+    if (dims[i] <= 0 || dims[i] > 0xFFFFFFFFLL) return false;
+    gdim[i] = (cuuint64_t)dims[i];
+    bdim[i] = (cuuint32_t)box[i];
+    estr[i] = 1;
+    if (box[i] > 256) return false;
+    if (i > 0) {
+      const long long bytes = strides[i - 1] * 4;
+      if (bytes % 16 != 0 || bytes <= 0 || bytes >= (1LL << 40)) return false;
+      gstr[i - 1] = (cuuint64_t)bytes;
+    }
+  }
+  CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr,
+                           bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    fprintf(stderr, "convnet_b200: cuTensorMapEncodeTiled failed (%d)\n", (int)r);
+    return false;
+  }
+  return true;
+}
+
+int pick_bn(int cols, int granule) {              // N-tile: as wide as possible, <= 256, balanced across tiles
+  const int tiles = ceil_div(cols, 256);
+  const int bn = ceil_div(ceil_div(cols, tiles), granule) * granule;
+  return std::min(256, std::max(granule, bn));
+}
+
+int tmem_cols_for(int bn) { int c = 32; while (c < 2 * bn) c *= 2; return c; }
+
+size_t smem_bytes_for(int bn, int stages) {
+  return 1024 + (size_t)stages * (kAStageBytes + (size_t)bn * BK * 4) + sizeof(SmemCtl) + 16;
+}
+
+int pick_stages(int bn) {
+  int s = kMaxStages;
+  while (s > 2 && smem_bytes_for(bn, s) > 225 * 1024) s--;
+  return s;
+}
+
+template <int OP>
+void launch(const CUtensorMap& a, const CUtensorMap& b, TcParams& p) {
+  p.stages = pick_stages(p.BN);
+  p.tmem_cols = tmem_cols_for(p.BN);
+  const size_t smem = smem_bytes_for(p.BN, p.stages);
+  static bool attr_set = false;
+  if (!attr_set) {
+    CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int grid = std::min(p.num_tiles, num_sms());
+  tc_conv_kernel<OP><<<grid, kThreads, smem, state().stream>>>(a, b, p);
+  count_launch();
+  CNB_LAUNCH_CHECK("tc_conv");
+}
+
+bool tc_enabled() {
+  static int en = -1;
+  if (en < 0) { const char* e = getenv("CONVNET_B200_DISABLE_TC"); en = (e && e[0] == '1') ? 0 : 1; }
+  return en == 1 && state().precision == kPrecTF32;
+}
+
+void fill_common(TcParams& p, const ConvGeom& g) {
+  p.N = g.N; p.nb = ceil_div(g.N, 32);
+  p.W = g.W; p.H = g.H; p.modX = g.modX; p.modY = g.modY; p.modules = g.modules;
+  p.Cin = g.Cin; p.Cout = g.Cout;
+  p.kx = g.kx; p.ky = g.ky; p.sx = g.sx; p.sy = g.sy; p.px = g.px; p.py = g.py; p.taps = g.kx * g.ky;
+  p.frames = g.frames; p.frame0 = 0;
+  p.splits = 1; p.units_per_split = 0;
+  p.out_frame_step = g.out_frame_step;
+}
+
+// image-like tensor (N, W, H, C[, frames]) as a 5-D map ordered (n, c, x, y, f) or (n, x, y, c, f)
+bool image_map(CUtensorMap* m, const float* base, const ConvGeom& g, int Wd, int Hd, int C, long long frame_step,
+               bool channel_second, int box_c) {
+  const long long N = g.N;
+  if (channel_second) {
+    const long long dims[5] = {N, C, Wd, Hd, g.frames};
+    const long long str[4] = {N * Wd * Hd, N, N * Wd, frame_step};
+    const int box[5] = {32, box_c, 1, 1, 1};
+    return make_map(m, base, 5, dims, str, box);
+  }
+  const long long dims[5] = {N, Wd, Hd, C, g.frames};
+  const long long str[4] = {N, N * Wd, N * Wd * Hd, frame_step};
+  const int box[5] = {32, 1, 1, box_c, 1};
+  return make_map(m, base, 5, dims, str, box);
+}
+
+}  // namespace
+
+// ---- fprop ---------------------------------------------------------------------------------------
+bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, float* targets, float st, float so) {
+  if (!tc_enabled() || !g.conv) return false;
+  if (g.N % 4 != 0 || g.Cout % 4 != 0 || g.Cin < 8) return false;          // TMA stride alignment / K efficiency
+  TcParams p; fill_common(p, g);
+  p.BN = pick_bn(g.Cout, 32);
+  p.kc_blocks = ceil_div(g.Cin, BK);
+  p.total_chunks = (long long)p.nb * g.modules * g.frames;
+  p.m_tiles = (int)ceil_div<long long>(p.total_chunks, 4);
+  p.n_tiles = ceil_div(g.Cout, p.BN);
+  p.num_tiles = p.m_tiles * p.n_tiles;
+  p.out = targets + (long long)g.cout0 * g.modules * g.N;
+  p.st = st; p.so = so;
+  p.idesc = ptx::make_idesc(2, true, true, BM, p.BN);
+  CUtensorMap ma, mb;
+  const float* img = images + (long long)g.cin0 * g.H * g.W * g.N;
+  // frames of a 3-D conv start in_frame_step floats apart and see Cin (= Cin3d*kt) channels
+  if (!image_map(&ma, img, g, g.W, g.H, g.Cin, g.in_frame_step, true, BK)) return false;
+  {
+    const long long dims[3] = {g.Cout, (long long)g.kx * g.ky, g.Cin};
+    const long long str[2] = {g.Cout, (long long)g.Cout * g.kx * g.ky};
+    const int box[3] = {32, 1, BK};
+    if (!make_map(&mb, filters, 3, dims, str, box)) return false;
+  }
+  launch<kFprop>(ma, mb, p);
+  state().last_conv_path = kPathTcTf32;
+  return true;
+}
+
+// ---- dgrad ---------------------------------------------------------------------------------------
+bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float st, float so) {
+  if (!tc_enabled() || !g.conv) return false;
+  if (g.N % 4 != 0 || g.Cout % 4 != 0 || g.Cout < 8 || g.Cin < 8) return false;
+  TcParams p; fill_common(p, g);
+  p.BN = pick_bn(g.Cin, 16);
+  p.kc_blocks = ceil_div(g.Cout, BK);
+  p.total_chunks = (long long)p.nb * g.W * g.H;
+  p.m_tiles = (int)ceil_div<long long>(p.total_chunks, 4);
+  p.n_tiles = ceil_div(g.Cin, p.BN);
+  p.num_tiles = p.m_tiles * p.n_tiles;
+  p.so = so;
+  p.idesc = ptx::make_idesc(2, true, false, BM, p.BN);
+  CUtensorMap ma, mb;
+  const float* der = derivs + (long long)g.cout0 * g.modules * g.N;
+  if (!image_map(&ma, der, g, g.modX, g.modY, g.Cout, g.out_frame_step, true, BK)) return false;
+  {
+    const long long dims[3] = {g.Cout, (long long)g.kx * g.ky, g.Cin};
+    const long long str[2] = {g.Cout, (long long)g.Cout * g.kx * g.ky};
+    const int box[3] = {32, 1, p.BN};
+    if (!make_map(&mb, filters, 3, dims, str, box)) return false;
+  }
+  float* out = targets + (long long)g.cin0 * g.H * g.W * g.N;
+  const bool whole = (g.frames == 1 && g.cin0 == 0 && g.Cin == g.CinT);
+  if (whole) {
+    p.st = st; p.out = out;
+    launch<kDgrad>(ma, mb, p);
+  } else {
+    // the reference scales the WHOLE target first (gemm.cu:760, conv3d_gemm.cu:98); frame windows overlap,
+    // so frames are accumulated by stream-ordered launches
+    scale_buffer(targets, g.img_total, st);
+    p.st = 1.f;
+    for (int f = 0; f < g.frames; f++) {
+      p.frame0 = f; p.out = out + f * g.in_frame_step;
+      launch<kDgrad>(ma, mb, p);
+    }
+  }
+  state().last_conv_path = kPathTcTf32;
+  return true;
+}
+
+// ---- wgrad ---------------------------------------------------------------------------------------
+bool tc_conv_outp(const ConvGeom& g, const float* images, const float* derivs, float* targets, float st, float so) {
+  if (!tc_enabled() || !g.conv) return false;
+  if (g.N % 4 != 0 || g.Cin < 8 || g.Cout < 8) return false;
+  TcParams p; fill_common(p, g);
+  p.BN = pick_bn(g.Cin, 16);
+  p.kc_blocks = 0;
+  p.total_chunks = 0;
+  p.m_tiles = ceil_div(g.Cout, BM);
+  p.n_tiles = ceil_div(g.Cin, p.BN);
+  const int units = g.modules * g.frames;
+  const long long base_tiles = (long long)p.taps * p.m_tiles * p.n_tiles;
+  int splits = (int)std::max<long long>(1, std::min<long long>(units, (2LL * num_sms()) / base_tiles));
+  const long long elems = (long long)g.Cout * g.K;
+  while (splits > 1 && elems * splits * 4 > (1LL << 30)) splits--;
+  p.units_per_split = ceil_div(units, splits);
+  p.splits = ceil_div(units, p.units_per_split);
+  p.num_tiles = (int)(base_tiles * p.splits);
+  p.st = st; p.so = so;
+  p.idesc = ptx::make_idesc(2, false, false, BM, p.BN);
+  CUtensorMap ma, mb;
+  const float* img = images + (long long)g.cin0 * g.H * g.W * g.N;
+  const float* der = derivs + (long long)g.cout0 * g.modules * g.N;
+  if (!image_map(&ma, der, g, g.modX, g.modY, g.Cout, g.out_frame_step, false, BM)) return false;
+  if (!image_map(&mb, img, g, g.W, g.H, g.Cin, g.in_frame_step, false, p.BN)) return false;
+  if (p.splits == 1) {
+    p.out = targets;
+    launch<kWgrad>(ma, mb, p);
+  } else {
+    float* part = (float*)workspace(sizeof(float) * elems * p.splits);
+    p.out = part;
+    launch<kWgrad>(ma, mb, p);
+    reduce_partials(part, targets, elems, 1, p.splits, st, so);
+  }
+  state().last_conv_path = kPathTcTf32;
+  return true;
+}
+
+}  // namespace cnb
