@@ -46,8 +46,8 @@ struct TcParams {
   int BN, stages, tmem_cols;
   int m_tiles, n_tiles, num_tiles;
   int kc_blocks;                    // ceil(K-side channels / 32)
-  long long total_chunks;           // fprop: nb*modules*frames ; dgrad: nb*W*H
-  int splits, units_per_split;      // wgrad: (frame,module) units per reduction split
+  int total_chunks;                 // fprop: nb*modules*frames ; dgrad: nb*W*H   (< 2^31, checked on the host)
+  int splits, units_per_split;      // wgrad: (frame, module-row) units per reduction split
   float* out;
   float st, so;
   long long out_frame_step;         // fprop: floats between output frames
@@ -63,17 +63,9 @@ struct __align__(8) SmemCtl {
 };
 
 // ------------------------------------------------------------------------------------------------
-// k-block enumeration, shared by the producer (which loads) and the MMA warp (which only counts)
+// tile / k-block enumeration, shared by the producer (which loads) and the MMA warp (which only counts).
+// All 32-bit arithmetic: one thread per CTA walks this, so every division counts.
 // ------------------------------------------------------------------------------------------------
-// dgrad: module coordinate touched by tap t at input coordinate X, or -1
-__device__ __forceinline__ int dgrad_mod(int X, int p, int t, int s, int mods) {
-  const int a = X - p - t;
-  if (a < 0) return -1;
-  const int m = a / s;
-  if (m * s != a || m >= mods) return -1;
-  return m;
-}
-
 template <int OP>
 struct Tile {
   int m_tile, n_tile;               // fprop/dgrad
@@ -97,47 +89,79 @@ __device__ __forceinline__ Tile<OP> decode_tile(const TcParams& p, int t) {
   return r;
 }
 
-// fprop / dgrad chunk -> (image block, position, frame)
-__device__ __forceinline__ void decode_chunk(const TcParams& p, long long q, int per_frame, int& ib, int& pos, int& f) {
-  ib = (int)(q % p.nb);
-  const long long r = q / p.nb;
-  pos = (int)(r % per_frame);
-  f = (int)(r / per_frame);
+// The four 32-row chunks of an fprop/dgrad m-tile: image offset, position (module / pixel) and frame.
+struct Chunks {
+  int n[4], pos[4], f[4];
+  bool ok[4];
+};
+__device__ __forceinline__ Chunks decode_chunks(const TcParams& p, int m_tile, int per_frame) {
+  Chunks c;
+#pragma unroll
+  for (int i = 0; i < 4; i++) {
+    const int q = m_tile * 4 + i;
+    c.ok[i] = q < p.total_chunks;
+    const int ib = q % p.nb, r = q / p.nb;
+    c.n[i] = c.ok[i] ? ib * 32 : p.N;        // n >= N: the whole TMA box is out of range -> zero-filled
+    c.pos[i] = r % per_frame;
+    c.f[i] = c.ok[i] ? r / per_frame : 0;
+  }
+  return c;
 }
 
-// dgrad: is tap (tx,ty) live for ANY chunk of this m-tile?
-__device__ __forceinline__ bool dgrad_tap_live(const TcParams& p, int m_tile, int tx, int ty) {
+// dgrad: module coordinate touched by tap t at input coordinate X, or -1
+__device__ __forceinline__ int dgrad_mod(int X, int p, int t, int s, int mods) {
+  const int a = X - p - t;
+  if (a < 0) return -1;
+  const int m = a / s;
+  if (m * s != a || m >= mods) return -1;
+  return m;
+}
+
+// dgrad: per-chunk bit masks of the taps that reach a module along x and along y (kx, ky <= 32)
+struct DgradTaps {
+  uint32_t xm[4], ym[4];
+  __device__ __forceinline__ bool live(int c, int tx, int ty) const { return ((xm[c] >> tx) & (ym[c] >> ty) & 1u) != 0; }
+  __device__ __forceinline__ bool any(int tx, int ty) const { return live(0, tx, ty) | live(1, tx, ty) | live(2, tx, ty) | live(3, tx, ty); }
+};
+__device__ __forceinline__ DgradTaps dgrad_taps(const TcParams& p, const Chunks& ch) {
+  DgradTaps d;
 #pragma unroll
   for (int c = 0; c < 4; c++) {
-    const long long q = (long long)m_tile * 4 + c;
-    if (q >= p.total_chunks) continue;
-    int ib, pix, f;
-    decode_chunk(p, q, p.W * p.H, ib, pix, f);
-    if (dgrad_mod(pix % p.W, p.px, tx, p.sx, p.modX) >= 0 && dgrad_mod(pix / p.W, p.py, ty, p.sy, p.modY) >= 0)
-      return true;
+    d.xm[c] = d.ym[c] = 0;
+    if (!ch.ok[c]) continue;
+    const int X = ch.pos[c] % p.W, Y = ch.pos[c] / p.W;
+    for (int t = 0; t < p.kx; t++) d.xm[c] |= (dgrad_mod(X, p.px, t, p.sx, p.modX) >= 0 ? 1u : 0u) << t;
+    for (int t = 0; t < p.ky; t++) d.ym[c] |= (dgrad_mod(Y, p.py, t, p.sy, p.modY) >= 0 ? 1u : 0u) << t;
   }
-  return false;
+  return d;
 }
-
-// wgrad: does tap (tx,ty) of module (mx,my) fall inside the image?
-__device__ __forceinline__ bool wgrad_unit_live(const TcParams& p, int mod, int tx, int ty) {
-  const int X = (mod % p.modX) * p.sx + p.px + tx, Y = (mod / p.modX) * p.sy + p.py + ty;
-  return (unsigned)X < (unsigned)p.W && (unsigned)Y < (unsigned)p.H;
-}
-
-template <int OP>
-__device__ __forceinline__ int count_kblocks(const TcParams& p, const Tile<OP>& t) {
-  if (OP == kFprop) return p.taps * p.kc_blocks;
-  if (OP == kDgrad) {
-    int live = 0;
-    for (int tap = 0; tap < p.taps; tap++) live += dgrad_tap_live(p, t.m_tile, tap % p.kx, tap / p.kx) ? 1 : 0;
-    return max(live, 1) * p.kc_blocks;
-  }
-  // wgrad
-  const int u0 = t.split * p.units_per_split, u1 = min(u0 + p.units_per_split, p.modules * p.frames);
+__device__ __forceinline__ int dgrad_live_taps(const TcParams& p, const DgradTaps& d) {
   int live = 0;
-  for (int u = u0; u < u1; u++) live += wgrad_unit_live(p, u % p.modules, t.tap % p.kx, t.tap / p.kx) ? 1 : 0;
-  return max(live, 1) * p.nb;
+  for (int ty = 0; ty < p.ky; ty++)
+    for (int tx = 0; tx < p.kx; tx++) live += d.any(tx, ty) ? 1 : 0;
+  return live;
+}
+
+// wgrad: the reduction of one tile runs over rows r = f*modY + my in [r0, r1) and, inside a row, over the
+// modules mx in [mx_lo, mx_hi] whose tap lands inside the image (the others contribute zeros and are skipped).
+struct WgradSpan { int r0, r1, mx_lo, mx_hi, live_rows; };
+__device__ __forceinline__ bool wgrad_row_live(const TcParams& p, int r, int ty) {
+  const int Y = (r % p.modY) * p.sy + p.py + ty;
+  return (unsigned)Y < (unsigned)p.H;
+}
+__device__ __forceinline__ WgradSpan wgrad_span(const TcParams& p, const Tile<kWgrad>& t) {
+  WgradSpan s;
+  const int tx = t.tap % p.kx, ty = t.tap / p.kx;
+  s.r0 = t.split * p.units_per_split;
+  s.r1 = min(s.r0 + p.units_per_split, p.modY * p.frames);
+  const int lo = -(p.px + tx);                             // mx*sx >= lo
+  s.mx_lo = lo <= 0 ? 0 : (lo + p.sx - 1) / p.sx;
+  const int hi = p.W - 1 - p.px - tx;                      // mx*sx <= hi
+  s.mx_hi = hi < 0 ? -1 : min(hi / p.sx, p.modX - 1);
+  s.live_rows = 0;
+  if (s.mx_hi >= s.mx_lo)
+    for (int r = s.r0; r < s.r1; r++) s.live_rows += wgrad_row_live(p, r, ty) ? 1 : 0;
+  return s;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -181,79 +205,81 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         auto end_stage = [&]() { if (++stage == p.stages) { stage = 0; phase ^= 1; } };
 
         if (OP == kFprop) {
-          // chunk coordinates of this m-tile
-          int cn[4], cX[4], cY[4], cF[4];
+          const Chunks ch = decode_chunks(p, tile.m_tile, p.modules);
+          int cX[4], cY[4];
 #pragma unroll
           for (int c = 0; c < 4; c++) {
-            const long long q = (long long)tile.m_tile * 4 + c;
-            if (q < p.total_chunks) {
-              int ib, mod, f; decode_chunk(p, q, p.modules, ib, mod, f);
-              cn[c] = ib * 32; cX[c] = (mod % p.modX) * p.sx + p.px; cY[c] = (mod / p.modX) * p.sy + p.py; cF[c] = f;
-            } else { cn[c] = p.N; cX[c] = 0; cY[c] = 0; cF[c] = 0; }    // n >= N: whole box zero-filled
+            cX[c] = (ch.pos[c] % p.modX) * p.sx + p.px;
+            cY[c] = (ch.pos[c] / p.modX) * p.sy + p.py;
           }
-          for (int tap = 0; tap < p.taps; tap++) {
-            const int tx = tap % p.kx, ty = tap / p.kx;
-            for (int cb = 0; cb < p.kc_blocks; cb++) {
-              uint8_t* a = begin_stage();
-              uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
+          for (int ty = 0; ty < p.ky; ty++)
+            for (int tx = 0; tx < p.kx; tx++) {
+              const int tap = tx + p.kx * ty;
+              for (int cb = 0; cb < p.kc_blocks; cb++) {
+                uint8_t* a = begin_stage();
+                uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
 #pragma unroll
-              for (int c = 0; c < 4; c++)
-                ptx::tma_load_5d(&mapA, &ctl->full[stage], a + c * (BK * 128), cn[c], cb * BK, cX[c] + tx, cY[c] + ty, cF[c]);
-              for (int j = 0; j < p.BN / 32; j++)
-                ptx::tma_load_3d(&mapB, &ctl->full[stage], b + j * (BK * 128), tile.n_tile * p.BN + j * 32, tap, cb * BK);
-              end_stage();
+                for (int c = 0; c < 4; c++)
+                  ptx::tma_load_5d(&mapA, &ctl->full[stage], a + c * (BK * 128), ch.n[c], cb * BK, cX[c] + tx, cY[c] + ty, ch.f[c]);
+                for (int j = 0; j < p.BN / 32; j++)
+                  ptx::tma_load_3d(&mapB, &ctl->full[stage], b + j * (BK * 128), tile.n_tile * p.BN + j * 32, tap, cb * BK);
+                end_stage();
+              }
             }
-          }
         } else if (OP == kDgrad) {
-          int cn[4], cX[4], cY[4];
+          const Chunks ch = decode_chunks(p, tile.m_tile, p.W * p.H);
+          const DgradTaps taps = dgrad_taps(p, ch);
+          const bool none = dgrad_live_taps(p, taps) == 0;       // then one all-zero k-block keeps the pipeline uniform
+          int cX[4], cY[4];
 #pragma unroll
-          for (int c = 0; c < 4; c++) {
-            const long long q = (long long)tile.m_tile * 4 + c;
-            if (q < p.total_chunks) {
-              int ib, pix, f; decode_chunk(p, q, p.W * p.H, ib, pix, f);
-              cn[c] = ib * 32; cX[c] = pix % p.W; cY[c] = pix / p.W;
-            } else { cn[c] = p.N; cX[c] = -1000000; cY[c] = -1000000; }
-          }
-          bool any = false;
-          for (int tap = 0; tap < p.taps; tap++) {
-            const int tx = tap % p.kx, ty = tap / p.kx;
-            bool live = dgrad_tap_live(p, tile.m_tile, tx, ty);
-            if (!live && !(tap == p.taps - 1 && !any)) continue;   // keep >= 1 k-block per tile (all-zero operands)
-            any = true;
-            int mx[4], my[4];
+          for (int c = 0; c < 4; c++) { cX[c] = ch.pos[c] % p.W; cY[c] = ch.pos[c] / p.W; }
+          for (int ty = 0; ty < p.ky; ty++)
+            for (int tx = 0; tx < p.kx; tx++) {
+              if (!(taps.any(tx, ty) || (none && tx == 0 && ty == 0))) continue;
+              int mx[4], my[4];
 #pragma unroll
-            for (int c = 0; c < 4; c++) {
-              mx[c] = dgrad_mod(cX[c], p.px, tx, p.sx, p.modX);
-              my[c] = dgrad_mod(cY[c], p.py, ty, p.sy, p.modY);
-              if (mx[c] < 0 || my[c] < 0 || !live) { mx[c] = -1; my[c] = -1; }      // out of range -> zeros
+              for (int c = 0; c < 4; c++) {
+                const bool lv = ch.ok[c] && taps.live(c, tx, ty);
+                mx[c] = lv ? (cX[c] - p.px - tx) / p.sx : -1;      // -1: out of range -> zeros
+                my[c] = lv ? (cY[c] - p.py - ty) / p.sy : -1;
+              }
+              const int tap = tx + p.kx * ty;
+              for (int ob = 0; ob < p.kc_blocks; ob++) {
+                uint8_t* a = begin_stage();
+                uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
+#pragma unroll
+                for (int c = 0; c < 4; c++)
+                  ptx::tma_load_5d(&mapA, &ctl->full[stage], a + c * (BK * 128), ch.n[c], ob * BK, mx[c], my[c], p.frame0);
+                ptx::tma_load_3d(&mapB, &ctl->full[stage], b, ob * BK, tap, tile.n_tile * p.BN);
+                end_stage();
+              }
             }
-            for (int ob = 0; ob < p.kc_blocks; ob++) {
-              uint8_t* a = begin_stage();
-              uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
-#pragma unroll
-              for (int c = 0; c < 4; c++)
-                ptx::tma_load_5d(&mapA, &ctl->full[stage], a + c * (BK * 128), cn[c], ob * BK, mx[c], my[c], p.frame0);
-              ptx::tma_load_3d(&mapB, &ctl->full[stage], b, ob * BK, tap, tile.n_tile * p.BN);
-              end_stage();
-            }
-          }
         } else {
+          const WgradSpan sp = wgrad_span(p, tile);
           const int tx = tile.tap % p.kx, ty = tile.tap / p.kx;
-          const int u0 = tile.split * p.units_per_split, u1 = min(u0 + p.units_per_split, p.modules * p.frames);
-          bool any = false;
-          for (int u = u0; u < u1; u++) {
-            const int mod = u % p.modules, f = u / p.modules;
-            const bool live = wgrad_unit_live(p, mod, tx, ty);
-            if (!live && !(u == u1 - 1 && !any)) continue;
-            any = true;
-            const int mx = mod % p.modX, my = mod / p.modX;
-            const int X = mx * p.sx + p.px + tx, Y = my * p.sy + p.py + ty;     // dead unit: X/Y out of range -> zeros
+          if (sp.live_rows == 0) {                         // nothing to sum: one zero k-block group
             for (int ib = 0; ib < p.nb; ib++) {
               uint8_t* a = begin_stage();
               uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
-              ptx::tma_load_5d(&mapA, &ctl->full[stage], a, ib * 32, mx, my, tile.o_tile * BM, f);
-              ptx::tma_load_5d(&mapB, &ctl->full[stage], b, ib * 32, X, Y, tile.c_tile * p.BN, f);
+              ptx::tma_load_5d(&mapA, &ctl->full[stage], a, ib * 32, 0, 0, tile.o_tile * BM, 0);
+              ptx::tma_load_5d(&mapB, &ctl->full[stage], b, ib * 32, -1, -1, tile.c_tile * p.BN, 0);
               end_stage();
+            }
+          } else {
+            for (int r = sp.r0; r < sp.r1; r++) {
+              if (!wgrad_row_live(p, r, ty)) continue;
+              const int f = r / p.modY, my = r % p.modY;
+              const int Y = my * p.sy + p.py + ty;
+              for (int mx = sp.mx_lo; mx <= sp.mx_hi; mx++) {
+                const int X = mx * p.sx + p.px + tx;
+                for (int ib = 0; ib < p.nb; ib++) {
+                  uint8_t* a = begin_stage();
+                  uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
+                  ptx::tma_load_5d(&mapA, &ctl->full[stage], a, ib * 32, mx, my, tile.o_tile * BM, f);
+                  ptx::tma_load_5d(&mapB, &ctl->full[stage], b, ib * 32, X, Y, tile.c_tile * p.BN, f);
+                  end_stage();
+                }
+              }
             }
           }
         }
@@ -263,14 +289,28 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // =============================== MMA issuer =================================
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
-    // operand descriptors: MN-major tiles are [chunk][BK rows][128 B] (LBO = chunk stride, K step = 8 rows = 1 KiB);
-    // K-major tiles are [row][128 B] (SBO = 8 rows = 1 KiB, K step = 32 B inside the swizzle atom)
+    // operand descriptors.
+    //  MN-major tf32 tiles are [chunk][BK rows][128 B] in SWIZZLE_128B_BASE32B: atoms of 4 K-rows x 128 B,
+    //    SBO = 512 B between 4-row groups, LBO = chunk stride, one UMMA (K = 8) = two groups = 1 KiB;
+    //  K-major tiles are [row][128 B] in SWIZZLE_128B: SBO = 8 rows = 1 KiB, K step = 32 B inside the atom.
     const bool a_mn = (OP != kWgrad), b_mn = (OP == kFprop);
     const uint32_t a_lbo = a_mn ? BK * 128 : 16, b_lbo = b_mn ? BK * 128 : 16;
+    const uint32_t a_sbo = a_mn ? 512 : 1024, b_sbo = b_mn ? 512 : 1024;
+    const uint32_t a_lay = a_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
+    const uint32_t b_lay = b_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
     const uint32_t a_kstep = a_mn ? 1024 : 32, b_kstep = b_mn ? 1024 : 32;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
       const Tile<OP> tile = decode_tile<OP>(p, t);
-      const int nkb = count_kblocks<OP>(p, tile);
+      int nkb;
+      if (OP == kFprop) {
+        nkb = p.taps * p.kc_blocks;
+      } else if (OP == kDgrad) {
+        const Chunks ch = decode_chunks(p, tile.m_tile, p.W * p.H);
+        nkb = max(dgrad_live_taps(p, dgrad_taps(p, ch)), 1) * p.kc_blocks;
+      } else {
+        const WgradSpan sp = wgrad_span(p, *reinterpret_cast<const Tile<kWgrad>*>(&tile));
+        nkb = max(sp.live_rows * (sp.mx_hi - sp.mx_lo + 1), 1) * p.nb;
+      }
       ptx::mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
       const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.BN);
@@ -282,8 +322,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const uint32_t b_addr = ptx::smem_u32(smemB + (size_t)stage * b_stage_bytes);
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ks++) {
-            const uint64_t da = ptx::make_smem_desc_sw128(a_addr + ks * a_kstep, a_lbo, 1024);
-            const uint64_t db = ptx::make_smem_desc_sw128(b_addr + ks * b_kstep, b_lbo, 1024);
+            const uint64_t da = ptx::make_smem_desc(a_addr + ks * a_kstep, a_lbo, a_sbo, a_lay);
+            const uint64_t db = ptx::make_smem_desc(b_addr + ks * b_kstep, b_lbo, b_sbo, b_lay);
             ptx::mma_tf32(d_tmem, da, db, p.idesc, (kb | ks) != 0);
           }
           ptx::mma_commit(&ctl->empty[stage]);              // frees the smem slot when these MMAs retire
@@ -306,10 +346,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int ncols_valid = 0;
       bool direct_scale = true;
       if (OP == kFprop || OP == kDgrad) {
-        const long long q = (long long)tile.m_tile * 4 + quarter;
+        const int q = tile.m_tile * 4 + quarter;
         const int per_frame = (OP == kFprop) ? p.modules : p.W * p.H;
         if (q < p.total_chunks) {
-          int ib, pos, f; decode_chunk(p, q, per_frame, ib, pos, f);
+          const int ib = q % p.nb, r = q / p.nb, pos = r % per_frame, f = r / per_frame;
           const int n = ib * 32 + lane;
           if (n < p.N) {
             col_stride = (long long)p.N * per_frame;
@@ -375,7 +415,7 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
 
 // fp32 tensor map; dims[0] is the contiguous axis; strides in ELEMENTS for dims 1..rank-1
 bool make_map(CUtensorMap* map, const float* base, int rank, const long long* dims, const long long* strides,
-              const int* box) {
+              const int* box, bool mn_major) {
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bdim[5], estr[5];
   if ((reinterpret_cast<uintptr_t>(base) & 15) != 0) return false;
@@ -392,7 +432,8 @@ bool make_map(CUtensorMap* map, const float* base, int rank, const long long* di
     }
   }
   CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr,
-                           bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                           bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fprintf(stderr, "convnet_b200: cuTensorMapEncodeTiled failed (%d)\n", (int)r);
@@ -459,12 +500,12 @@ bool image_map(CUtensorMap* m, const float* base, const ConvGeom& g, int Wd, int
     const long long dims[5] = {N, C, Wd, Hd, g.frames};
     const long long str[4] = {N * Wd * Hd, N, N * Wd, frame_step};
     const int box[5] = {32, box_c, 1, 1, 1};
-    return make_map(m, base, 5, dims, str, box);
+    return make_map(m, base, 5, dims, str, box, true);
   }
   const long long dims[5] = {N, Wd, Hd, C, g.frames};
   const long long str[4] = {N, N * Wd, N * Wd * Hd, frame_step};
   const int box[5] = {32, 1, 1, box_c, 1};
-  return make_map(m, base, 5, dims, str, box);
+  return make_map(m, base, 5, dims, str, box, false);
 }
 
 }  // namespace
@@ -476,8 +517,10 @@ bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, fl
   TcParams p; fill_common(p, g);
   p.BN = pick_bn(g.Cout, 32);
   p.kc_blocks = ceil_div(g.Cin, BK);
-  p.total_chunks = (long long)p.nb * g.modules * g.frames;
-  p.m_tiles = (int)ceil_div<long long>(p.total_chunks, 4);
+  const long long chunks = (long long)p.nb * g.modules * g.frames;
+  if (chunks * 4 >= (1LL << 31)) return false;
+  p.total_chunks = (int)chunks;
+  p.m_tiles = ceil_div(p.total_chunks, 4);
   p.n_tiles = ceil_div(g.Cout, p.BN);
   p.num_tiles = p.m_tiles * p.n_tiles;
   p.out = targets + (long long)g.cout0 * g.modules * g.N;
@@ -491,7 +534,7 @@ bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, fl
     const long long dims[3] = {g.Cout, (long long)g.kx * g.ky, g.Cin};
     const long long str[2] = {g.Cout, (long long)g.Cout * g.kx * g.ky};
     const int box[3] = {32, 1, BK};
-    if (!make_map(&mb, filters, 3, dims, str, box)) return false;
+    if (!make_map(&mb, filters, 3, dims, str, box, true)) return false;
   }
   launch<kFprop>(ma, mb, p);
   state().last_conv_path = kPathTcTf32;
@@ -505,8 +548,10 @@ bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, 
   TcParams p; fill_common(p, g);
   p.BN = pick_bn(g.Cin, 16);
   p.kc_blocks = ceil_div(g.Cout, BK);
-  p.total_chunks = (long long)p.nb * g.W * g.H;
-  p.m_tiles = (int)ceil_div<long long>(p.total_chunks, 4);
+  const long long chunks = (long long)p.nb * g.W * g.H;
+  if (chunks * 4 >= (1LL << 31) || g.kx > 32 || g.ky > 32) return false;
+  p.total_chunks = (int)chunks;
+  p.m_tiles = ceil_div(p.total_chunks, 4);
   p.n_tiles = ceil_div(g.Cin, p.BN);
   p.num_tiles = p.m_tiles * p.n_tiles;
   p.so = so;
@@ -518,7 +563,7 @@ bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, 
     const long long dims[3] = {g.Cout, (long long)g.kx * g.ky, g.Cin};
     const long long str[2] = {g.Cout, (long long)g.Cout * g.kx * g.ky};
     const int box[3] = {32, 1, p.BN};
-    if (!make_map(&mb, filters, 3, dims, str, box)) return false;
+    if (!make_map(&mb, filters, 3, dims, str, box, false)) return false;
   }
   float* out = targets + (long long)g.cin0 * g.H * g.W * g.N;
   const bool whole = (g.frames == 1 && g.cin0 == 0 && g.Cin == g.CinT);
@@ -549,7 +594,7 @@ bool tc_conv_outp(const ConvGeom& g, const float* images, const float* derivs, f
   p.total_chunks = 0;
   p.m_tiles = ceil_div(g.Cout, BM);
   p.n_tiles = ceil_div(g.Cin, p.BN);
-  const int units = g.modules * g.frames;
+  const int units = g.modY * g.frames;               // reduction units = module rows
   const long long base_tiles = (long long)p.taps * p.m_tiles * p.n_tiles;
   int splits = (int)std::max<long long>(1, std::min<long long>(units, (2LL * num_sms()) / base_tiles));
   const long long elems = (long long)g.Cout * g.K;

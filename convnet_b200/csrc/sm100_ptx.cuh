@@ -138,14 +138,19 @@ __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.
 
 // ---- descriptors ---------------------------------------------------------------------------------
 // Shared-memory matrix descriptor (cute/arch/mma_sm100_desc.hpp SmemDescriptor): start>>4 [0,14),
-// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64).
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout type [61,64):
+//   2 = SWIZZLE_128B          (16-byte chunks XOR row%8; K-major operands, and MN-major 16-bit operands)
+//   1 = SWIZZLE_128B_BASE32B  (32-byte chunks XOR row%4; the ONLY layout for MN-major tf32 operands,
+//                              cutlass/gemm/collective/builders/sm100_common.inl:92; TMA: SWIZZLE_128B_ATOM_32B)
+constexpr uint32_t kLayoutSw128 = 2, kLayoutSw128Base32 = 1;
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;
-  d |= (uint64_t)2 << 61;
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 // Instruction descriptor (InstrDescriptor, same header): c_format F32=1 [4,6), a/b_format [7,10)/[10,13)
