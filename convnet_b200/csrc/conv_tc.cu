@@ -66,15 +66,14 @@ struct __align__(8) SmemCtl {
 // tile / k-block enumeration, shared by the producer (which loads) and the MMA warp (which only counts).
 // All 32-bit arithmetic: one thread per CTA walks this, so every division counts.
 // ------------------------------------------------------------------------------------------------
-template <int OP>
 struct Tile {
   int m_tile, n_tile;               // fprop/dgrad
   int tap, o_tile, c_tile, split;   // wgrad
 };
 
 template <int OP>
-__device__ __forceinline__ Tile<OP> decode_tile(const TcParams& p, int t) {
-  Tile<OP> r;
+__device__ __forceinline__ Tile decode_tile(const TcParams& p, int t) {
+  Tile r;
   if (OP == kWgrad) {
     r.split = t % p.splits; t /= p.splits;
     r.c_tile = t % p.n_tiles; t /= p.n_tiles;
@@ -149,7 +148,7 @@ __device__ __forceinline__ bool wgrad_row_live(const TcParams& p, int r, int ty)
   const int Y = (r % p.modY) * p.sy + p.py + ty;
   return (unsigned)Y < (unsigned)p.H;
 }
-__device__ __forceinline__ WgradSpan wgrad_span(const TcParams& p, const Tile<kWgrad>& t) {
+__device__ __forceinline__ WgradSpan wgrad_span(const TcParams& p, const Tile& t) {
   WgradSpan s;
   const int tx = t.tap % p.kx, ty = t.tap / p.kx;
   s.r0 = t.split * p.units_per_split;
@@ -196,7 +195,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int stage = 0; uint32_t phase = 0;
       const uint32_t tx_bytes = kAStageBytes + b_stage_bytes;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const Tile<OP> tile = decode_tile<OP>(p, t);
+        const Tile tile = decode_tile<OP>(p, t);
         auto begin_stage = [&]() -> uint8_t* {
           ptx::mbar_wait(&ctl->empty[stage], phase ^ 1);
           ptx::mbar_arrive_expect_tx(&ctl->full[stage], tx_bytes);
@@ -300,7 +299,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t b_lay = b_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
     const uint32_t a_kstep = a_mn ? 1024 : 32, b_kstep = b_mn ? 1024 : 32;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const Tile<OP> tile = decode_tile<OP>(p, t);
+      const Tile tile = decode_tile<OP>(p, t);
       int nkb;
       if (OP == kFprop) {
         nkb = p.taps * p.kc_blocks;
@@ -308,7 +307,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const Chunks ch = decode_chunks(p, tile.m_tile, p.W * p.H);
         nkb = max(dgrad_live_taps(p, dgrad_taps(p, ch)), 1) * p.kc_blocks;
       } else {
-        const WgradSpan sp = wgrad_span(p, *reinterpret_cast<const Tile<kWgrad>*>(&tile));
+        const WgradSpan sp = wgrad_span(p, tile);
         nkb = max(sp.live_rows * (sp.mx_hi - sp.mx_lo + 1), 1) * p.nb;
       }
       ptx::mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
@@ -339,7 +338,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const Tile<OP> tile = decode_tile<OP>(p, t);
+      const Tile tile = decode_tile<OP>(p, t);
       // row owned by this thread and the address of its column 0
       float* row_ptr = nullptr;
       long long col_stride = 0;
