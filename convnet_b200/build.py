@@ -64,5 +64,30 @@ def build(force=False, verbose=False):
     return LIB
 
 
+HOST = os.path.join(HERE, "host")
+HOST_LIB = os.path.join(LIBDIR, "libconvnet_b200_host.so")
+HOST_SOURCES = ["matrix.cc", "edge.cc", "convnet.cc", "models.cc", "capi.cc"]
+
+
+def build_host(force=False):
+    """host C++ (Matrix / Edge / ConvNet / GradChecker / DataParallelSync) -> libconvnet_b200_host.so"""
+    build(force=False)
+    h = hashlib.sha256()
+    for f in sorted(os.listdir(HOST)):
+        h.update(open(os.path.join(HOST, f), "rb").read())
+    h.update(open(os.path.join(LIBDIR, ".stamp")).read().encode())
+    stamp_file = os.path.join(LIBDIR, ".stamp_host")
+    if not force and os.path.exists(HOST_LIB) and os.path.exists(stamp_file) and open(stamp_file).read() == h.hexdigest():
+        return HOST_LIB
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", "-fvisibility=hidden", "-I/usr/local/cuda/include",
+           "-o", HOST_LIB] + [os.path.join(HOST, f) for f in HOST_SOURCES] + [
+           "-L" + LIBDIR, "-lconvnet_b200", "-Wl,-rpath,$ORIGIN", "-L/usr/local/cuda/lib64", "-lcudart_static",
+           "-ldl", "-lrt", "-lpthread"]
+    subprocess.run(cmd, check=True)
+    open(stamp_file, "w").write(h.hexdigest())
+    return HOST_LIB
+
+
 if __name__ == "__main__":
+    build_host(force="--force" in sys.argv)
     print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

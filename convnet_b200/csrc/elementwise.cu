@@ -90,6 +90,56 @@ __global__ void sgd_kernel(float* w, float* h, const float* __restrict__ g, long
   }
 }
 
+__device__ __forceinline__ uint32_t hash_u32(unsigned long long x) {     // splitmix64 finaliser
+  x += 0x9E3779B97F4A7C15ULL; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL; x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return (uint32_t)((x ^ (x >> 31)) >> 32);
+}
+__global__ void dropout_kernel(float* x, float* mask, long long n, float dropprob, float scale, unsigned long long seed) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const float u = hash_u32(seed + (unsigned long long)i) * (1.0f / 4294967296.0f);
+    const float m = u >= dropprob ? scale : 0.f;
+    mask[i] = m;
+    x[i] *= m;
+  }
+}
+__global__ void mult_kernel(float* a, const float* __restrict__ b, long long n) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] *= b[i];
+}
+
+// softmax over classes of a column-major [rows x cols] matrix: one thread per image, reads strided by rows
+// (coalesced across images); three passes over <= a few thousand classes.
+__global__ void softmax_kernel(float* x, int rows, int cols) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= rows) return;
+  float m = -INFINITY;
+  for (int c = 0; c < cols; c++) m = fmaxf(m, x[n + (long long)rows * c]);
+  float s = 0.f;
+  for (int c = 0; c < cols; c++) { const float e = __expf(x[n + (long long)rows * c] - m); x[n + (long long)rows * c] = e; s += e; }
+  const float inv = 1.f / s;
+  for (int c = 0; c < cols; c++) x[n + (long long)rows * c] *= inv;
+}
+__global__ void softmax_ce_deriv_kernel(const float* __restrict__ p, const int* __restrict__ labels, float* deriv,
+                                        float* loss, int rows, int cols) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= rows) return;
+  const int lab = labels[n];
+  for (int c = 0; c < cols; c++) deriv[n + (long long)rows * c] = p[n + (long long)rows * c] - (c == lab ? 1.f : 0.f);
+  if (loss) loss[n] = -__logf(fmaxf(p[n + (long long)rows * lab], 1e-30f));
+}
+__global__ void sum_kernel(const float* __restrict__ a, float* out, int n) {   // single block
+  float s = 0.f;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) s += a[i];
+  __shared__ float sh[32];
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    s = threadIdx.x < (blockDim.x >> 5) ? sh[threadIdx.x] : 0.f;
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (threadIdx.x == 0) *out = s;
+  }
+}
+
 }  // namespace cnb
 
 using namespace cnb;
@@ -121,6 +171,30 @@ void cnb_relu_deriv(float* dx, const float* y, long long n) {
   if (n <= 0) return;
   relu_deriv_kernel<<<blocks_for(n, 256), 256, 0, state().stream>>>(dx, y, n);
   count_launch(); CNB_LAUNCH_CHECK("relu_deriv");
+}
+void cnb_dropout(float* x, float* mask, long long n, float dropprob, float scale, unsigned long long seed) {
+  if (n <= 0) return;
+  dropout_kernel<<<blocks_for(n, 256), 256, 0, state().stream>>>(x, mask, n, dropprob, scale, seed);
+  count_launch(); CNB_LAUNCH_CHECK("dropout");
+}
+void cnb_mult(float* a, const float* b, long long n) {
+  if (n <= 0) return;
+  mult_kernel<<<blocks_for(n, 256), 256, 0, state().stream>>>(a, b, n);
+  count_launch(); CNB_LAUNCH_CHECK("mult");
+}
+void cnb_softmax(float* x, int rows, int cols) {
+  if (rows <= 0) return;
+  softmax_kernel<<<ceil_div(rows, 128), 128, 0, state().stream>>>(x, rows, cols);
+  count_launch(); CNB_LAUNCH_CHECK("softmax");
+}
+void cnb_softmax_ce_deriv(const float* probs, const int* labels, float* deriv, float* loss_per_image, int rows, int cols) {
+  if (rows <= 0) return;
+  softmax_ce_deriv_kernel<<<ceil_div(rows, 128), 128, 0, state().stream>>>(probs, labels, deriv, loss_per_image, rows, cols);
+  count_launch(); CNB_LAUNCH_CHECK("softmax_ce_deriv");
+}
+void cnb_sum(const float* a, float* out, int n) {
+  sum_kernel<<<1, 256, 0, state().stream>>>(a, out, n);
+  count_launch(); CNB_LAUNCH_CHECK("sum");
 }
 void cnb_sgd_momentum(float* w, float* hist, const float* grad, long long n, float lr, float momentum, float l2) {
   if (n <= 0) return;

@@ -1,0 +1,366 @@
+// convnet.cc — see convnet.h.
+#include "convnet.h"
+
+#include <dlfcn.h>
+#include <nccl.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+
+#ifndef DIVUP
+#define DIVUP(x, y) (((x) + (y)-1) / (y))
+#endif
+
+namespace cnbhost {
+
+#define HOST_CUDA_CHECK(expr)                                                                         \
+  do {                                                                                                \
+    cudaError_t _e = (expr);                                                                          \
+    if (_e != cudaSuccess) {                                                                          \
+      fprintf(stderr, "%s(%d) : CUDA error : %s : %s\n", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      exit(EXIT_FAILURE);                                                                             \
+    }                                                                                                 \
+  } while (0)
+
+// =================================================================== Layer
+Layer::~Layer() { if (labels_) cudaFree(labels_); }
+
+void Layer::AllocateMemory(int batch_size) {               // layer.cc:228-262 (Shape4D convention :257-258)
+  const int cols = image_size_y_ * image_size_x_ * image_size_t_ * config_.num_channels;
+  state_.AllocateGPUMemory(batch_size, cols);
+  state_.SetShape4D(batch_size, image_size_x_, image_size_y_, config_.num_channels * image_size_t_);
+  if (!config_.is_input) {
+    deriv_.AllocateGPUMemory(batch_size, cols);
+    deriv_.SetShape4D(batch_size, image_size_x_, image_size_y_, config_.num_channels * image_size_t_);
+  }
+  if (config_.dropprob > 0) dropout_mask_.AllocateGPUMemory(batch_size, cols);
+  if (config_.is_output) {
+    HOST_CUDA_CHECK(cudaMalloc((void**)&labels_, sizeof(int) * batch_size));
+    HOST_CUDA_CHECK(cudaMemset(labels_, 0, sizeof(int) * batch_size));
+    loss_per_image_.AllocateGPUMemory(batch_size, 1);
+  }
+}
+
+void Layer::ApplyActivation() {
+  switch (config_.activation) {
+    case LINEAR: break;
+    case RECTIFIED_LINEAR: state_.ApplyReLU(); break;      // LowerBound(0), layer.cc:550
+    case SOFTMAX: state_.ApplySoftmax(); break;
+  }
+}
+void Layer::ApplyDerivativeOfActivation() {
+  if (config_.activation == RECTIFIED_LINEAR) deriv_.ApplyDerivOfReLU(state_);
+}
+void Layer::ApplyDropout(bool train, unsigned long long step) {      // layer.cc:367-395, scale-up at train time
+  if (config_.dropprob <= 0 || !train) return;
+  const unsigned long long seed = (std::hash<std::string>()(config_.name) ^ (step * 0x9E3779B97F4A7C15ULL));
+  cnb_dropout(state_.GetDevData(), dropout_mask_.GetDevData(), (long long)state_.GetNumEls(), config_.dropprob,
+              1.0f / (1.0f - config_.dropprob), seed);
+}
+void Layer::ApplyDerivativeofDropout() {
+  if (config_.dropprob <= 0 || config_.is_input) return;
+  cnb_mult(deriv_.GetDevData(), dropout_mask_.GetDevData(), (long long)deriv_.GetNumEls());
+}
+void Layer::ComputeDeriv() {
+  cnb_softmax_ce_deriv(state_.GetDevData(), labels_, deriv_.GetDevData(), loss_per_image_.GetDevData(),
+                       state_.GetRows(), state_.GetCols());
+}
+
+// =================================================================== DataParallelSync (NCCL, loaded lazily)
+namespace {
+struct NcclApi {
+  void* handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Bcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  const char* (*GetErrorString)(ncclResult_t) = nullptr;
+  bool ok = false;
+};
+NcclApi& nccl() {
+  static NcclApi api;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    // torch's bundled libnccl.so.2 is already mapped when the launcher imported torch; otherwise the loader path is used
+    api.handle = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!api.handle) { fprintf(stderr, "convnet_b200 host: cannot load libnccl.so.2: %s\n", dlerror()); return api; }
+#define LOAD(field, sym) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, sym))
+    LOAD(GetUniqueId, "ncclGetUniqueId"); LOAD(CommInitRank, "ncclCommInitRank"); LOAD(CommDestroy, "ncclCommDestroy");
+    LOAD(AllReduce, "ncclAllReduce"); LOAD(Bcast, "ncclBroadcast"); LOAD(GetErrorString, "ncclGetErrorString");
+#undef LOAD
+    api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.Bcast;
+  }
+  return api;
+}
+#define NCCL_CHECK(expr)                                                                               \
+  do {                                                                                                 \
+    ncclResult_t _r = (expr);                                                                          \
+    if (_r != ncclSuccess) {                                                                           \
+      fprintf(stderr, "%s(%d) : NCCL error : %s : %s\n", __FILE__, __LINE__, #expr,                    \
+              nccl().GetErrorString ? nccl().GetErrorString(_r) : "?");                                \
+      exit(EXIT_FAILURE);                                                                              \
+    }                                                                                                  \
+  } while (0)
+}  // namespace
+
+DataParallelSync::DataParallelSync() {}
+DataParallelSync::~DataParallelSync() {
+  if (comm_ && nccl().CommDestroy) nccl().CommDestroy((ncclComm_t)comm_);
+  if (comm_stream_) cudaStreamDestroy(comm_stream_);
+  if (ready_) cudaEventDestroy(ready_);
+  if (done_) cudaEventDestroy(done_);
+}
+bool DataParallelSync::GetUniqueId(char out[128]) {
+  if (!nccl().ok) return false;
+  ncclUniqueId id;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  NCCL_CHECK(nccl().GetUniqueId(&id));
+  memcpy(out, &id, 128);
+  return true;
+}
+bool DataParallelSync::Init(int rank, int world, const char idbytes[128]) {
+  if (!nccl().ok) return false;
+  rank_ = rank; world_ = world;
+  ncclUniqueId id;
+  memcpy(&id, idbytes, 128);
+  ncclComm_t c;
+  NCCL_CHECK(nccl().CommInitRank(&c, world, id, rank));
+  comm_ = c;
+  HOST_CUDA_CHECK(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking));
+  HOST_CUDA_CHECK(cudaEventCreateWithFlags(&ready_, cudaEventDisableTiming));
+  HOST_CUDA_CHECK(cudaEventCreateWithFlags(&done_, cudaEventDisableTiming));
+  return true;
+}
+void DataParallelSync::Broadcast(float* buf, size_t count) {
+  if (world_ <= 1) return;
+  HOST_CUDA_CHECK(cudaEventRecord(ready_, Matrix::Stream()));
+  HOST_CUDA_CHECK(cudaStreamWaitEvent(comm_stream_, ready_, 0));
+  NCCL_CHECK(nccl().Bcast(buf, buf, count, ncclFloat, 0, (ncclComm_t)comm_, comm_stream_));
+  pending_ = true;
+  WaitAll();
+}
+void DataParallelSync::AllReduceAverageAsync(float* buf, size_t offset, size_t count) {
+  if (world_ <= 1 || count == 0) return;
+  HOST_CUDA_CHECK(cudaEventRecord(ready_, Matrix::Stream()));          // gradients of this bucket are final
+  HOST_CUDA_CHECK(cudaStreamWaitEvent(comm_stream_, ready_, 0));
+  NCCL_CHECK(nccl().AllReduce(buf + offset, buf + offset, count, ncclFloat, ncclAvg, (ncclComm_t)comm_, comm_stream_));
+  pending_ = true;
+}
+void DataParallelSync::WaitAll() {
+  if (!pending_) return;
+  HOST_CUDA_CHECK(cudaEventRecord(done_, comm_stream_));
+  HOST_CUDA_CHECK(cudaStreamWaitEvent(Matrix::Stream(), done_, 0));
+  pending_ = false;
+}
+
+// =================================================================== ConvNet
+ConvNet::ConvNet(const ModelConfig& model, int batch_size) : model_(model), batch_size_(batch_size) {
+  // BuildNet (convnet.cc:150-270), restricted to chains: edge i connects layer i to layer i+1
+  if (model.layer.size() != model.edge.size() + 1) { fprintf(stderr, "ConvNet: model must be a chain\n"); exit(1); }
+  for (const LayerConfig& lc : model.layer) layers_.push_back(new Layer(lc));
+  for (size_t i = 0; i < model.edge.size(); i++) {
+    Edge* e = Edge::ChooseEdgeClass(model.edge[i]);
+    e->SetSource(layers_[i]); e->SetDest(layers_[i + 1]);
+    e->SetInputChannels(layers_[i]->GetNumChannels());
+    e->SetOutputChannels(layers_[i + 1]->GetNumChannels());
+    e->SetBatchSize(batch_size);
+    edges_.push_back(e);
+  }
+  // SetImageSize propagation (convnet.cc:226-268)
+  const LayerConfig& in = model.layer.front();
+  layers_[0]->SetSize(in.image_size_y, in.image_size_x, in.image_size_t);
+  for (size_t i = 0; i < edges_.size(); i++) {
+    edges_[i]->SetImageSize(layers_[i]->GetSizeY(), layers_[i]->GetSizeX(), layers_[i]->GetSizeT());
+    layers_[i + 1]->SetSize(edges_[i]->GetNumModulesY(), edges_[i]->GetNumModulesX(), edges_[i]->GetNumModulesT());
+  }
+}
+
+ConvNet::~ConvNet() {
+  for (Edge* e : edges_) delete e;
+  for (Layer* l : layers_) delete l;
+}
+
+void ConvNet::AllocateMemory() {
+  for (Layer* l : layers_) l->AllocateMemory(batch_size_);
+  // AllocateEdgeMemory (convnet.cc:272-298): one flat buffer, each edge's slice padded to 128 floats
+  size_t total = 0;
+  for (Edge* e : edges_) {
+    size_t req = e->GetParameterMemoryRequirement();
+    edge_offset_.push_back(total);
+    edge_size_.push_back(req);
+    total += DIVUP(req, (size_t)128) * 128;
+  }
+  num_params_ = total;
+  if (total == 0) total = 128;
+  parameters_.AllocateGPUMemory(1, (int)total);
+  grad_parameters_.AllocateGPUMemory(1, (int)total);
+  history_.AllocateGPUMemory(1, (int)total);
+  loss_sum_.AllocateGPUMemory(1, 1);
+  for (size_t i = 0; i < edges_.size(); i++) {
+    if (edge_size_[i] == 0) continue;
+    Matrix p, g, h;
+    parameters_.GetSlice(p, (int)edge_offset_[i], (int)(edge_offset_[i] + edge_size_[i]));
+    grad_parameters_.GetSlice(g, (int)edge_offset_[i], (int)(edge_offset_[i] + edge_size_[i]));
+    history_.GetSlice(h, (int)edge_offset_[i], (int)(edge_offset_[i] + edge_size_[i]));
+    edges_[i]->SetMemory(p);
+    edges_[i]->SetGradMemory(g);
+    edges_[i]->SetHistoryMemory(h);
+    edges_[i]->Initialize(model_.seed + 17 * (unsigned)i);
+  }
+  HOST_CUDA_CHECK(cudaStreamSynchronize(Matrix::Stream()));
+}
+
+void ConvNet::Fprop(bool train) {                            // convnet.cc:377-388
+  for (size_t i = 1; i < layers_.size(); i++) {
+    Layer* l = layers_[i];
+    Edge* e = edges_[i - 1];
+    e->ComputeUp(layers_[i - 1]->GetState(), l->GetState(), /*overwrite=*/true, train);
+    l->ApplyActivation();
+    l->ApplyDropout(train, step_);
+  }
+}
+
+void ConvNet::ComputeDeriv() { OutputLayer().ComputeDeriv(); }
+
+float ConvNet::GetLoss() {                                   // CrossEntropyMultinomial::GetLoss: sum over the batch
+  Layer& out = OutputLayer();
+  cnb_softmax_ce_deriv(out.GetState().GetDevData(), out.GetLabels(), out.GetDeriv().GetDevData(),
+                       out.GetLossPerImage(), batch_size_, out.GetState().GetCols());
+  cnb_sum(out.GetLossPerImage(), loss_sum_.GetDevData(), batch_size_);
+  return loss_sum_.ReadValue(0);
+}
+
+void ConvNet::Bprop() {                                      // convnet.cc:390-405 + 362-375
+  for (int i = (int)layers_.size() - 1; i >= 1; i--) {
+    Layer* out = layers_[i];
+    Layer* in = layers_[i - 1];
+    Edge* e = edges_[i - 1];
+    // (the reference runs these two at the top of the NEXT loop iteration, i.e. before this layer's edges)
+    if (!out->IsOutput()) { out->ApplyDerivativeofDropout(); out->ApplyDerivativeOfActivation(); }
+    e->ComputeOuter(in->GetState(), out->GetDeriv());
+    if (!in->IsInput()) e->ComputeDown(out->GetDeriv(), in->GetState(), out->GetState(), in->GetDeriv(), /*overwrite=*/true);
+    // data-parallel: ship every bucket whose last gradient just became final (side stream, overlaps the rest of bprop)
+    if (dp_ && dp_->world() > 1)
+      for (const Bucket& b : buckets_)
+        if (b.trigger == i - 1) dp_->AllReduceAverageAsync(grad_parameters_.GetDevData(), b.lo, b.hi - b.lo);
+  }
+}
+
+void ConvNet::UpdateWeights() {                              // convnet.cc:440-450
+  if (dp_) dp_->WaitAll();                                   // replaces Accumulate + Broadcast (MPI through host memory)
+  for (Edge* e : edges_) e->UpdateWeights();
+}
+
+void ConvNet::TrainOneBatch(float* loss_out) {               // convnet.cc:475-485 (GetBatch is the caller's H2D copy)
+  Fprop(true);
+  ComputeDeriv();
+  if (loss_out) {                                            // GetLoss: one scalar D2H per step, like the reference
+    cnb_sum(OutputLayer().GetLossPerImage(), loss_sum_.GetDevData(), batch_size_);
+  }
+  Bprop();
+  UpdateWeights();
+  if (loss_out) *loss_out = loss_sum_.ReadValue(0);
+  step_++;
+}
+
+std::vector<Bucket> PlanBuckets(const std::vector<size_t>& edge_offset, const std::vector<size_t>& edge_size,
+                                size_t bucket_floats) {
+  std::vector<Bucket> out;
+  size_t lo = 0, hi = 0;
+  bool open = false;
+  int last_weighted = -1;
+  for (int i = (int)edge_size.size() - 1; i >= 0; i--) {
+    if (edge_size[i] == 0) continue;
+    const size_t e_lo = edge_offset[i], e_hi = e_lo + DIVUP(edge_size[i], (size_t)128) * 128;
+    if (!open) { hi = e_hi; open = true; }
+    lo = e_lo;
+    last_weighted = i;
+    if (hi - lo >= bucket_floats) { out.push_back({lo, hi, i}); open = false; }
+  }
+  if (open) out.push_back({lo, hi, last_weighted});
+  return out;
+}
+
+void ConvNet::SetDataParallel(DataParallelSync* dp, size_t bucket_floats) {
+  dp_ = dp;
+  buckets_ = PlanBuckets(edge_offset_, edge_size_, bucket_floats);
+}
+void ConvNet::BroadcastParameters() { if (dp_) dp_->Broadcast(parameters_.GetDevData(), parameters_.GetNumEls()); }
+
+double ConvNet::FlopsFprop() const {
+  double f = 0;
+  for (Edge* e : edges_) f += e->FlopsUp();
+  return f;
+}
+double ConvNet::FlopsTrainStep() const {                     // 3x fprop minus the dgrad into the input layer
+  double f = 0;
+  for (size_t i = 0; i < edges_.size(); i++) f += edges_[i]->FlopsUp() * (i == 0 ? 2.0 : 3.0);
+  return f;
+}
+
+// =================================================================== GradChecker (src/grad_check.cc)
+float GradChecker::LossAt(Matrix& w, size_t index, float value) {
+  w.WriteValue(index, value);
+  Fprop(false);
+  return GetLoss();
+}
+
+std::vector<GradCheckResult> GradChecker::Run(unsigned seed) {
+  // random inputs / labels (grad_check.cc:82-90)
+  std::mt19937 gen(seed);
+  std::normal_distribution<float> nd(0.f, 1.f);
+  Matrix& x = InputLayer().GetState();
+  std::vector<float> hx(x.GetNumEls());
+  for (float& v : hx) v = nd(gen);
+  x.CopyFromHost(hx.data(), hx.size());
+  std::vector<int> hl(batch_size_);
+  const int classes = OutputLayer().GetState().GetCols();
+  for (int& v : hl) v = (int)(gen() % classes);
+  HOST_CUDA_CHECK(cudaMemcpy(OutputLayer().GetLabels(), hl.data(), sizeof(int) * batch_size_, cudaMemcpyHostToDevice));
+
+  Fprop(false);
+  ComputeDeriv();
+  Bprop();                                                    // analytical gradients now in grad_weights of each edge
+
+  std::vector<GradCheckResult> results;
+  for (Edge* ed : edges_) {
+    if (!ed->Config().grad_check) continue;
+    EdgeWithWeight* e = dynamic_cast<EdgeWithWeight*>(ed);
+    if (!e) continue;
+    std::vector<float> eps = ed->Config().grad_check_epsilon;
+    if (eps.empty()) eps = {1e-2f, 1e-3f, 1e-4f};
+    auto check = [&](Matrix& w, Matrix& gw, float epsilon) -> float {     // grad_check.cc:20-61
+      int n = std::min<int>(ed->Config().grad_check_num_params, (int)w.GetNumEls());
+      std::vector<float> analytical(gw.GetNumEls());
+      gw.CopyToHost(analytical.data(), analytical.size());
+      float diff_sum = 0; int non_zero = 0;
+      for (int i = 0; i < n; i++) {
+        const float val = w.ReadValue(i);
+        const float e1 = LossAt(w, i, val + epsilon);
+        const float e2 = LossAt(w, i, val - epsilon);
+        w.WriteValue(i, val);
+        const float numeric = (e1 - e2) / (batch_size_ * 2 * epsilon);
+        const float diff = analytical[i] - numeric, scale = (analytical[i] + numeric) / 2;
+        if (!(scale == 0 && diff == 0)) { diff_sum += std::fabs(diff / scale); non_zero++; }
+      }
+      return non_zero ? diff_sum / non_zero : 0.f;
+    };
+    GradCheckResult best{e->GetName(), 0.f, 1e30f, 1e30f};
+    for (float ep : eps) {                                     // first epsilon that passes wins (grad_check.cc:43-66)
+      GradCheckResult r{e->GetName(), ep, check(e->GetWeight(), e->GetGradWeight(), ep), 0.f};
+      r.mean_scaled_diff_b = e->GetBias().GetNumEls() ? check(e->GetBias(), e->GetGradBias(), ep) : 0.f;
+      if (std::max(r.mean_scaled_diff_w, r.mean_scaled_diff_b) < std::max(best.mean_scaled_diff_w, best.mean_scaled_diff_b)) best = r;
+      if (r.mean_scaled_diff_w < 0.01f && r.mean_scaled_diff_b < 0.01f) break;
+    }
+    results.push_back(best);
+  }
+  return results;
+}
+
+}  // namespace cnbhost

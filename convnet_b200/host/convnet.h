@@ -1,0 +1,160 @@
+// convnet.h — the slice of the reference's ConvNet that sequences the hot path
+// (src/convnet.{h,cc}: BuildNet :150, AllocateEdgeMemory :272-298, Fprop :377, Bprop :390,
+// UpdateWeights :440-450, TrainOneBatch :475-485), its GradChecker (src/grad_check.cc) and the
+// data-parallel gradient sync that replaces the reference's host-staged MPI
+// Accumulate + Broadcast (src/convnet.cc:407-438) with in-place NCCL all-reduce over NVLink.
+//
+// Layers form a chain (every BASELINE net is one: Appendix B of SURVEY.md).  The model comes
+// from a ModelConfig struct (protobuf / pbtxt parsing is out of scope);
+// builders for the BASELINE configs live in models.cc.
+#pragma once
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "edge.h"
+
+namespace cnbhost {
+
+enum Activation { LINEAR, RECTIFIED_LINEAR, SOFTMAX };
+
+struct LayerConfig {
+  std::string name;
+  int num_channels = 0;
+  bool is_input = false, is_output = false;
+  Activation activation = LINEAR;
+  int image_size_y = 0, image_size_x = 0, image_size_t = 1;   // input layer only
+  float dropprob = 0.f;
+};
+
+struct ModelConfig {
+  std::string name;
+  std::vector<LayerConfig> layer;
+  std::vector<EdgeConfig> edge;
+  unsigned seed = 42;
+};
+
+class Layer {                                   // src/layer.{h,cc}, reduced to state/deriv + activation
+ public:
+  explicit Layer(const LayerConfig& c) : config_(c), image_size_y_(0), image_size_x_(0), image_size_t_(1) {}
+  void SetSize(int y, int x, int t) { image_size_y_ = y; image_size_x_ = x; image_size_t_ = t; }
+  void AllocateMemory(int batch_size);
+  void ApplyActivation();                       // layer.cc:545-560
+  void ApplyDerivativeOfActivation();           // layer.cc:562-580
+  void ApplyDropout(bool train, unsigned long long step);   // layer.cc:  mask = rand > dropprob ; state *= mask
+  void ApplyDerivativeofDropout();
+  void ComputeDeriv();                          // softmax + cross-entropy: deriv = p - onehot   (loss_functions.cc)
+  Matrix& GetState() { return state_; }
+  Matrix& GetDeriv() { return deriv_; }
+  int* GetLabels() { return labels_; }
+  float* GetLossPerImage() { return loss_per_image_.GetDevData(); }
+  bool IsInput() const { return config_.is_input; }
+  bool IsOutput() const { return config_.is_output; }
+  int GetNumChannels() const { return config_.num_channels; }
+  int GetSizeY() const { return image_size_y_; }
+  int GetSizeX() const { return image_size_x_; }
+  int GetSizeT() const { return image_size_t_; }
+  const std::string& GetName() const { return config_.name; }
+  ~Layer();
+
+ private:
+  LayerConfig config_;
+  int image_size_y_, image_size_x_, image_size_t_;
+  Matrix state_, deriv_, loss_per_image_, dropout_mask_;
+  int* labels_ = nullptr;
+};
+
+// NCCL all-reduce of the flat gradient buffer, bucketed along edge boundaries and launched on a side
+// stream as soon as the gradients of a bucket are final, so the exchange hides under back-propagation.
+class DataParallelSync {
+ public:
+  DataParallelSync();
+  ~DataParallelSync();
+  static bool GetUniqueId(char out[128]);                       // rank 0; bytes are broadcast by the launcher
+  bool Init(int rank, int world, const char id[128]);
+  int world() const { return world_; }
+  int rank() const { return rank_; }
+  void Broadcast(float* buf, size_t count);                     // initial parameters from rank 0 (convnet.cc:300-309)
+  // average buf[offset, offset+count) over ranks, ordered after everything already on the compute stream
+  void AllReduceAverageAsync(float* buf, size_t offset, size_t count);
+  void WaitAll();                                               // compute stream waits for every pending all-reduce
+ private:
+  void* comm_ = nullptr;
+  cudaStream_t comm_stream_ = nullptr;
+  cudaEvent_t ready_ = nullptr, done_ = nullptr;
+  int rank_ = 0, world_ = 1;
+  bool pending_ = false;
+};
+
+// Gradient buckets for the overlapped all-reduce.  Back-propagation finalises edge gradients from the LAST
+// edge to the first, and edge slices are adjacent in the flat buffer (128-float padded), so a bucket is the
+// contiguous range [lo, hi) that becomes final when edge `trigger` has run ComputeOuter.  Buckets are closed
+// once they hold >= bucket_floats; every parameter belongs to exactly one bucket.
+struct Bucket { size_t lo, hi; int trigger; };
+std::vector<Bucket> PlanBuckets(const std::vector<size_t>& edge_offset, const std::vector<size_t>& edge_size,
+                                size_t bucket_floats);
+
+class ConvNet {
+ public:
+  ConvNet(const ModelConfig& model, int batch_size);
+  virtual ~ConvNet();
+  void AllocateMemory();                                        // convnet.cc:272-298: ONE flat parameter / gradient buffer
+  virtual void Fprop(bool train);                               // convnet.cc:377-388
+  virtual void Bprop();                                         // convnet.cc:390-405
+  virtual void UpdateWeights();                                 // convnet.cc:440-450
+  void ComputeDeriv();
+  void TrainOneBatch(float* loss_out);                          // convnet.cc:475-485
+  float GetLoss();                                              // sum of per-image CE (synchronises)
+  void SetDataParallel(DataParallelSync* dp, size_t bucket_floats);
+  void BroadcastParameters();
+
+  Layer& InputLayer() { return *layers_.front(); }
+  Layer& OutputLayer() { return *layers_.back(); }
+  std::vector<Edge*>& Edges() { return edges_; }
+  std::vector<Layer*>& Layers() { return layers_; }
+  Matrix& Parameters() { return parameters_; }
+  Matrix& GradParameters() { return grad_parameters_; }
+  size_t NumParameters() const { return num_params_; }
+  int BatchSize() const { return batch_size_; }
+  double FlopsFprop() const;
+  double FlopsTrainStep() const;                                // fprop + wgrad for every weighted edge + dgrad except into the input
+  const std::vector<size_t>& EdgeOffsets() const { return edge_offset_; }
+  const std::vector<size_t>& EdgeSizes() const { return edge_size_; }
+  float* DeviceLoss() { return loss_sum_.GetDevData(); }
+
+ protected:
+  ModelConfig model_;
+  int batch_size_;
+  std::vector<Layer*> layers_;
+  std::vector<Edge*> edges_;                    // edges_[i]: layers_[i] -> layers_[i+1]
+  Matrix parameters_, grad_parameters_, history_, loss_sum_;
+  std::vector<size_t> edge_offset_, edge_size_;
+  size_t num_params_ = 0;
+  DataParallelSync* dp_ = nullptr;
+  std::vector<Bucket> buckets_;
+  unsigned long long step_ = 0;
+};
+
+// src/grad_check.{h,cc}: finite-difference check of dLoss/dparam for the first k weights and biases
+// of every edge flagged grad_check, through the whole net.
+struct GradCheckResult {
+  std::string edge;
+  float epsilon;
+  float mean_scaled_diff_w, mean_scaled_diff_b;     // pass if < 0.01 (grad_check.cc:61)
+};
+class GradChecker : public ConvNet {
+ public:
+  GradChecker(const ModelConfig& model, int batch_size) : ConvNet(model, batch_size) {}
+  std::vector<GradCheckResult> Run(unsigned seed);
+ private:
+  float LossAt(Matrix& w, size_t index, float value);
+};
+
+// models.cc
+ModelConfig BuildAlexNet();     // examples/imagenet/CLS_net_20140801232522.pbtxt
+ModelConfig BuildLeNet();       // examples/mnist-conv/net.pbtxt
+ModelConfig BuildC3D();
+ModelConfig BuildTinyNet();     // small conv+pool+rnorm+1x1+fc net for tests / grad check
+ModelConfig BuildModel(const std::string& name);
+
+}  // namespace cnbhost

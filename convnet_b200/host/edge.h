@@ -1,0 +1,207 @@
+// edge.h — the Edge operator API of the reference (src/edge.h:20-190, src/edge_with_weight.h:10-58)
+// and the six edge types on the BASELINE configs' path, on top of the host Matrix facade.
+//
+//   ConvEdge            src/conv_edge.{h,cc}            conv -> shared bias ; wgrad -> bias grad
+//   MaxPoolEdge         src/maxpool_edge.{h,cc}
+//   AvgPoolEdge         src/avgpool_edge.{h,cc}
+//   ResponseNormEdge    src/response_norm_edge.{h,cc}
+//   FCEdge              src/fc_edge.{h,cc}              (reference: Matrix::Dot / cublasSgemm)
+//   ConvOneToOneEdge    src/conv_onetoone_edge.{h,cc}   (reference: Matrix::Dot / cublasSgemm)
+// FC and 1x1 edges run on the same implicit-GEMM conv kernels (a 1x1 convolution IS that GEMM),
+// SURVEY.md §8(f) rank 1.  The protobuf `config::Edge` is replaced by the plain EdgeConfig struct
+// (protobuf is not in the image); field names follow proto/convnet_config.proto:120-221.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "matrix.h"
+
+namespace cnbhost {
+
+class Layer;
+
+enum EdgeType { FC, CONVOLUTIONAL, MAXPOOL, AVGPOOL, RESPONSE_NORM, CONV_ONETOONE };
+
+struct OptimizerConfig {             // proto/convnet_config.proto Optimizer (SGD subset, src/optimizer.cc:174-200)
+  float epsilon = 0.01f;
+  float momentum = 0.9f;
+  float l2_decay = 0.f;
+};
+
+struct EdgeConfig {
+  std::string name, source, dest;
+  EdgeType edge_type = FC;
+  int kernel_size = 1, stride = 1, padding = 0;
+  int kernel_size_y = 0, kernel_size_x = 0, stride_y = 0, stride_x = 0, padding_y = -1, padding_x = -1;   // 0/-1: unset
+  int kernel_size_t = 1, stride_t = 1, padding_t = 0;
+  bool shared_bias = true, has_no_bias = false;
+  float add_scale = 0.0005f, pow_scale = 0.75f, frac_of_filters_response_norm = 0.25f;
+  bool response_norm_in_blocks = false;
+  float scale_gradients = 1.f;
+  float init_wt = 0.f;               // 0: DENSE_UNIFORM_SQRT_FAN_IN (edge_with_weight.cc:120-128)
+  OptimizerConfig weight_optimizer, bias_optimizer;
+  bool grad_check = false;
+  int grad_check_num_params = 10;
+  std::vector<float> grad_check_epsilon;
+};
+
+class Edge {
+ public:
+  explicit Edge(const EdgeConfig& c);
+  virtual ~Edge() {}
+  static Edge* ChooseEdgeClass(const EdgeConfig& c);                     // src/edge.cc:17-60
+  static ConvDesc GetConvDesc(const EdgeConfig& c);                      // src/edge.cc:87-106 (negates padding)
+  static void GetNumModules(const ConvDesc d, int image_size_y, int image_size_x, int image_size_t,
+                            int& num_modules_y, int& num_modules_x, int& num_modules_t);   // src/edge.cc:108-114
+
+  virtual void ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) = 0;
+  virtual void ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input,
+                           bool overwrite) = 0;
+  virtual void ComputeOuter(Matrix& input, Matrix& deriv_output) {}
+  virtual void UpdateWeights() {}
+  virtual void SetMemory(Matrix& p) {}
+  virtual void SetGradMemory(Matrix& p) {}
+  virtual void SetHistoryMemory(Matrix& p) {}
+  virtual size_t GetParameterMemoryRequirement() { return 0; }
+  virtual void Initialize(unsigned seed) {}
+  virtual bool HasNoParameters() const { return true; }
+  virtual void SetImageSize(int image_size_y, int image_size_x, int image_size_t);
+  virtual double FlopsUp() const { return 0; }                           // 2*MACs per batch
+
+  int GetNumModulesY() const { return num_modules_y_; }
+  int GetNumModulesX() const { return num_modules_x_; }
+  int GetNumModulesT() const { return num_modules_t_; }
+  void SetInputChannels(int a) { num_input_channels_ = a; }
+  void SetOutputChannels(int a) { num_output_channels_ = a; }
+  int GetNumOutputChannels() const { return num_output_channels_; }
+  const std::string& GetName() const { return name_; }
+  const EdgeConfig& Config() const { return config_; }
+  Layer* GetSource() { return source_; }
+  Layer* GetDest() { return dest_; }
+  void SetSource(Layer* l) { source_ = l; }
+  void SetDest(Layer* l) { dest_ = l; }
+  void SetBatchSize(int n) { batch_size_ = n; }
+
+ protected:
+  EdgeConfig config_;
+  std::string name_;
+  Layer *source_, *dest_;
+  int num_input_channels_, num_output_channels_;
+  int image_size_y_, image_size_x_, image_size_t_;
+  int num_modules_y_, num_modules_x_, num_modules_t_;
+  int batch_size_;
+};
+
+class EdgeWithWeight : public Edge {
+ public:
+  explicit EdgeWithWeight(const EdgeConfig& c) : Edge(c), has_no_bias_(c.has_no_bias), scale_gradients_(c.scale_gradients), num_grads_received_(0) {}
+  bool HasNoParameters() const override { return false; }
+  void UpdateWeights() override;                                         // src/edge_with_weight.cc:96-118
+  void SetHistoryMemory(Matrix& p) override;
+  void Initialize(unsigned seed) override;
+  Matrix& GetWeight() { return weights_; }
+  Matrix& GetGradWeight() { return grad_weights_; }
+  Matrix& GetBias() { return bias_; }
+  Matrix& GetGradBias() { return grad_bias_; }
+  int GetNumGradsReceived() const { return num_grads_received_; }
+  void IncrementNumGradsReceived() { num_grads_received_++; }
+  void NotifyStart() { num_grads_received_ = 0; }
+  virtual int FanIn() const = 0;
+
+ protected:
+  Matrix weights_, grad_weights_, bias_, grad_bias_, hist_weights_, hist_bias_;
+  bool has_no_bias_;
+  float scale_gradients_;
+  int num_grads_received_;
+};
+
+class ConvEdge : public EdgeWithWeight {
+ public:
+  explicit ConvEdge(const EdgeConfig& c);
+  void SetImageSize(int y, int x, int t) override;
+  size_t GetParameterMemoryRequirement() override;
+  void SetMemory(Matrix& p) override;
+  void SetGradMemory(Matrix& p) override;
+  void ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) override;
+  void ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) override;
+  void ComputeOuter(Matrix& input, Matrix& deriv_output) override;
+  double FlopsUp() const override;
+  int FanIn() const override;
+  ConvDesc GetConvDesc() const { return conv_desc_; }
+
+ private:
+  ConvDesc conv_desc_;
+  int partial_sum_y_, partial_sum_x_;
+  bool shared_bias_;
+};
+
+class FCEdge : public EdgeWithWeight {          // weights [Cout x K] column-major, like a conv filter bank
+ public:
+  explicit FCEdge(const EdgeConfig& c) : EdgeWithWeight(c) {}
+  void SetImageSize(int y, int x, int t) override;
+  size_t GetParameterMemoryRequirement() override;
+  void SetMemory(Matrix& p) override;
+  void SetGradMemory(Matrix& p) override;
+  void ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) override;
+  void ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) override;
+  void ComputeOuter(Matrix& input, Matrix& deriv_output) override;
+  double FlopsUp() const override;
+  int FanIn() const override { return num_inputs_; }
+
+ private:
+  void View(Matrix& in, Matrix& out);
+  int num_inputs_ = 0;
+  ConvDesc desc_;
+};
+
+class ConvOneToOneEdge : public EdgeWithWeight {
+ public:
+  explicit ConvOneToOneEdge(const EdgeConfig& c) : EdgeWithWeight(c) {}
+  void SetImageSize(int y, int x, int t) override;
+  size_t GetParameterMemoryRequirement() override;
+  void SetMemory(Matrix& p) override;
+  void SetGradMemory(Matrix& p) override;
+  void ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) override;
+  void ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) override;
+  void ComputeOuter(Matrix& input, Matrix& deriv_output) override;
+  double FlopsUp() const override;
+  int FanIn() const override { return num_input_channels_; }
+
+ private:
+  ConvDesc desc_;
+};
+
+class MaxPoolEdge : public Edge {
+ public:
+  explicit MaxPoolEdge(const EdgeConfig& c) : Edge(c), conv_desc_(Edge::GetConvDesc(c)) {}
+  void SetImageSize(int y, int x, int t) override;
+  void ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) override;
+  void ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) override;
+
+ protected:
+  ConvDesc conv_desc_;
+};
+
+class AvgPoolEdge : public MaxPoolEdge {
+ public:
+  explicit AvgPoolEdge(const EdgeConfig& c) : MaxPoolEdge(c) {}
+  void ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) override;
+  void ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) override;
+};
+
+class ResponseNormEdge : public Edge {
+ public:
+  explicit ResponseNormEdge(const EdgeConfig& c)
+      : Edge(c), num_filters_response_norm_(0), blocked_(c.response_norm_in_blocks), add_scale_(c.add_scale),
+        pow_scale_(c.pow_scale), frac_of_filters_response_norm_(c.frac_of_filters_response_norm) {}
+  void SetImageSize(int y, int x, int t) override;
+  void ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) override;
+  void ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) override;
+
+ private:
+  int num_filters_response_norm_;
+  bool blocked_;
+  float add_scale_, pow_scale_, frac_of_filters_response_norm_;
+};
+
+}  // namespace cnbhost

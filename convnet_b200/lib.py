@@ -79,6 +79,11 @@ SIGNATURES = {
     "cnb_relu": [FP, ct.c_longlong],
     "cnb_relu_deriv": [FP, FP, ct.c_longlong],
     "cnb_sgd_momentum": [FP, FP, FP, ct.c_longlong, F, F, F],
+    "cnb_dropout": [FP, FP, ct.c_longlong, F, F, ct.c_ulonglong],
+    "cnb_mult": [FP, FP, ct.c_longlong],
+    "cnb_softmax": [FP, I, I],
+    "cnb_softmax_ce_deriv": [FP, FP, FP, FP, I, I],
+    "cnb_sum": [FP, FP, I],
 }
 RESTYPES = {
     "convnet_b200_version": I, "convnet_b200_get_stream": ct.c_void_p,

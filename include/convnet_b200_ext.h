@@ -62,6 +62,19 @@ void cnb_channel_bias_grad(const float* derivs, float* grad_bias, long long rows
 /* x = max(x, 0) ; dx *= (y > 0) */
 void cnb_relu(float* x, long long n);
 void cnb_relu_deriv(float* dx, const float* y, long long n);
+/* binary dropout (Layer::ApplyDropoutAtTrainTime, src/layer.cc:367-395): mask[i] = Bernoulli(1-dropprob)*scale,
+ * x *= mask; counter-based RNG keyed by (seed, i).  cnb_mult: a *= b (ApplyDerivativeofDropout). */
+void cnb_dropout(float* x, float* mask, long long n, float dropprob, float scale, unsigned long long seed);
+void cnb_mult(float* a, const float* b, long long n);
+/* softmax over the classes of a column-major [rows=N x cols=classes] matrix, in place
+ * (Layer::ApplyActivation for SOFTMAX layers, src/layer.cc) */
+void cnb_softmax(float* x, int rows, int cols);
+/* deriv = probs - onehot(labels); loss_per_image[n] = -log probs[n, label] (may be NULL)
+ * (CrossEntropyMultinomial, src/loss_functions.cc:70-95) */
+void cnb_softmax_ce_deriv(const float* probs, const int* labels, float* deriv, float* loss_per_image,
+                          int rows, int cols);
+/* *out = sum(a[0..n)) on the device (no host sync) */
+void cnb_sum(const float* a, float* out, int n);
 /* SGD with momentum and L2 decay, one fused pass (src/optimizer.cc:174-200):
  *   g' = lr*(g + l2*w);  h = momentum*h + g';  w -= h */
 void cnb_sgd_momentum(float* w, float* hist, const float* grad, long long n, float lr,

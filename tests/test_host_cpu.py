@@ -1,0 +1,94 @@
+"""CPU-only tests of the host-side logic of the data-parallel path: the gradient-bucket plan computed by the native
+host code, and (world_size 2, gloo) that averaging the flat gradient buffer bucket by bucket in plan order
+reproduces the reference's Accumulate + Broadcast semantics (mean of the per-rank gradients, src/convnet.cc:407-450)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def host():
+    from convnet_b200 import build, net
+    build.build_host()
+    net.load_host()
+    return net
+
+
+def test_alexnet_parameter_layout_matches_reference(host):
+    sizes = host.model_edge_params("alexnet")
+    assert len(sizes) == 19
+    # weights + one shared bias per output channel
+    assert sizes[0] == 96 * (147 + 1) and sizes[3] == 256 * (2400 + 1) and sizes[16] == 4096 * (18432 + 1)
+    assert sizes[1] == sizes[2] == 0                      # pool / rnorm edges have no parameters
+    assert sum(sizes) == 104321000                        # "104.3 M parameters"
+    assert host.model_edge_params("lenet") == [48 * 17, 0, 128 * (16 * 48 + 1), 0, 10 * (1152 + 1)]
+
+
+@pytest.mark.parametrize("model", ["alexnet", "lenet", "c3d", "tiny"])
+@pytest.mark.parametrize("bucket", [1, 1 << 16, 8 << 20, 1 << 30])
+def test_bucket_plan_partitions_the_flat_buffer(host, model, bucket):
+    sizes = host.model_edge_params(model)
+    plan, total = host.plan_buckets(sizes, bucket)
+    assert total % 128 == 0
+    # back-to-front, contiguous, exact cover
+    assert plan[0][1] == total and plan[-1][0] == 0
+    for (lo, hi, trig), (lo2, hi2, trig2) in zip(plan, plan[1:]):
+        assert lo == hi2 and trig > trig2
+    for lo, hi, trig in plan:
+        assert hi > lo and sizes[trig] > 0
+        # a bucket may only be sent once its LOWEST edge (the trigger) has produced its gradient
+        off = sum((s + 127) // 128 * 128 for s in sizes[:trig])
+        assert off == lo
+    if bucket == 1 << 30:
+        assert len(plan) == 1
+    if bucket == 1:
+        assert len(plan) == sum(1 for s in sizes if s > 0)
+
+
+WORKER = r'''
+import os, sys, numpy as np, torch, torch.distributed as dist
+sys.path.insert(0, sys.argv[1])
+from convnet_b200 import net
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+dist.init_process_group("gloo", rank=rank, world_size=world)
+sizes = net.model_edge_params("lenet")
+plan, total = net.plan_buckets(sizes, 4096)
+g = torch.from_numpy(np.random.RandomState(100 + rank).randn(total).astype(np.float32))
+ref = [torch.from_numpy(np.random.RandomState(100 + r).randn(total).astype(np.float32)) for r in range(world)]
+for lo, hi, trig in plan:                  # what DataParallelSync::AllReduceAverageAsync does per bucket (ncclAvg)
+    dist.all_reduce(g[lo:hi], op=dist.ReduceOp.SUM); g[lo:hi] /= world
+want = sum(ref) / world
+assert torch.allclose(g, want, atol=1e-6), (g - want).abs().max()
+out = [torch.zeros_like(g) for _ in range(world)]
+dist.all_gather(out, g)
+assert all(torch.equal(o, out[0]) for o in out)      # bit-identical on every rank -> replicas stay in lock-step
+dist.barrier(); dist.destroy_process_group()
+print("OK", rank)
+'''
+
+
+def test_bucketed_average_world2_gloo(host, tmp_path):
+    script = tmp_path / "w.py"
+    script.write_text(WORKER)
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    procs = []
+    for r in range(2):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE="2", MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, str(script), ROOT], env=env, stdout=subprocess.PIPE,
+                                      stderr=subprocess.STDOUT, text=True))
+    outs = [p.communicate(timeout=180)[0] for p in procs]
+    assert all(p.returncode == 0 for p in procs), outs
+    assert all("OK" in o for o in outs)
+
+
+def test_bench_reference_arm_non_root_ranks_exit_quietly():
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
+                       env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0 and r.stdout.strip() == ""

@@ -1,0 +1,125 @@
+"""CPU arm of the bench: the reference's own CPU implementation of the hot path
+(eigenmat/cpumat_conv.cc through oracle/_ref/libeigenmat_ref.so; the C restatement
+oracle/libconv_oracle.so when _ref is not there) running the AlexNet training step's conv / 1x1 / fc
+work — fprop, dgrad (not into the input layer) and wgrad of every weighted edge of
+CLS_net_20140801232522 — on the host cores.  Pooling / response-norm / elementwise steps are
+<0.1 % of the CPU time and are left out (stated in the `sample` field).
+
+TEST/BENCH INFRASTRUCTURE: this is the baseline being measured NEXT TO the product, never part of it.
+The reference's conv path is single-threaded (naive sgemm), so `cores` worker
+processes each push their own images through it: that is "all the host threads it can use".
+"""
+import multiprocessing as mp
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+# (name, W, H, Cin, Cout, k, stride, pad) — SURVEY.md Appendix B; fc layers are 1x1 convs on a 1x1 image
+ALEXNET_WEIGHTED = [
+    ("conv1", 224, 224, 3, 96, 7, 2, 1), ("conv2", 55, 55, 96, 256, 5, 2, 1), ("nin2_1", 27, 27, 256, 256, 1, 1, 0),
+    ("conv3", 14, 14, 256, 384, 3, 1, 1), ("nin3_1", 14, 14, 384, 768, 1, 1, 0), ("conv4", 14, 14, 768, 384, 3, 1, 1),
+    ("nin4_1", 14, 14, 384, 768, 1, 1, 0), ("nin4_2", 14, 14, 768, 384, 1, 1, 0), ("conv5", 14, 14, 384, 512, 3, 1, 0),
+    ("nin5_1", 12, 12, 512, 1024, 1, 1, 0), ("nin5_2", 12, 12, 1024, 512, 1, 1, 0),
+    ("fc6", 1, 1, 18432, 4096, 1, 1, 0), ("fc7", 1, 1, 4096, 4096, 1, 1, 0), ("fc8", 1, 1, 4096, 1000, 1, 1, 0),
+]
+
+
+def _backend():
+    from oracle_lib import Oracle, RefLib
+    if RefLib.available():
+        return RefLib(), "reference"
+    return Oracle(), "port"
+
+
+SUBSET = ("conv3", "nin3_1", "fc7")      # one 3x3 conv, one 1x1 conv, one fc: the bounded sample for short time budgets
+
+
+def flops_per_image(layers=None):
+    f = 0.0
+    for i, (name, W, H, Cin, Cout, k, s, p) in enumerate(ALEXNET_WEIGHTED):
+        if layers is not None and name not in layers:
+            continue
+        mod = (W + 2 * p - k) // s + 1
+        f += 2.0 * mod * mod * Cout * k * k * Cin * (2 if i == 0 else 3)
+    return f
+
+
+def run_step(n_images, seed=0, layers=None):
+    """one AlexNet training step's conv/fc work for a batch of n_images on ONE core; returns seconds."""
+    from convnet_b200.abi import GetConvDesc
+    lib, _ = _backend()
+    r = np.random.RandomState(seed)
+    F = lambda a: np.asfortranarray(a.astype(np.float32))
+    t0 = time.perf_counter()
+    for i, (name, W, H, Cin, Cout, k, s, p) in enumerate(ALEXNET_WEIGHTED):
+        if layers is not None and name not in layers:
+            continue
+        mod = (W + 2 * p - k) // s + 1
+        d = GetConvDesc(Cin, Cout, k, k, s, s, p, p)
+        ish, fsh, tsh = (n_images, W, H, Cin), (Cout, k, k, Cin), (n_images, mod, mod, Cout)
+        x = F(r.standard_normal((n_images, W * H * Cin)))
+        w = F(r.standard_normal((Cout, k * k * Cin)) * 0.01)
+        dy = F(r.standard_normal((n_images, mod * mod * Cout)))
+        y = np.zeros((n_images, mod * mod * Cout), dtype=np.float32, order="F")
+        lib.convUp(x, w, y, ish, fsh, tsh, d, 0.0, 1.0)
+        dw = np.zeros_like(w)
+        lib.convOutp(x, dy, dw, ish, tsh, fsh, d, 0.0, 1.0 / n_images)
+        if i > 0:
+            dx = np.zeros_like(x)
+            lib.convDown(dy, w, dx, tsh, fsh, ish, d, 0.0, 1.0)
+    return time.perf_counter() - t0
+
+
+def _worker(args):
+    n_images, seed, layers = args
+    os.environ["OMP_NUM_THREADS"] = "1"
+    return run_step(n_images, seed, layers)
+
+
+class Pool:
+    """worker processes kept alive across bench steps"""
+
+    def __init__(self, cores=None):
+        self.cores = cores or os.cpu_count() or 1
+        self.pool = mp.get_context("spawn").Pool(self.cores)
+        _, self.kind = _backend()
+
+    def close(self):
+        self.pool.close(); self.pool.join()
+
+    def step(self, images_per_core=1, full=True):
+        """one bounded sample: every core pushes images_per_core image(s) through the step (full layer list, or
+        the SUBSET extrapolated by FLOPs). Returns (images_per_second, description)."""
+        layers = None if full else SUBSET
+        t0 = time.perf_counter()
+        per = self.pool.map(_worker, [(images_per_core, 100 + i, layers) for i in range(self.cores)])
+        wall = time.perf_counter() - t0
+        images = images_per_core * self.cores
+        frac = flops_per_image(layers) / flops_per_image(None)
+        value = images * frac / max(per)       # every core finishes its share within max(per) seconds
+        what = "all 14 weighted edges" if full else "layers %s (%.1f%% of the step's FLOPs, images/s extrapolated by FLOPs)" % (
+            "+".join(SUBSET), 100 * frac)
+        desc = ("AlexNet (CLS_net_20140801232522) training step on the host CPU: conv/1x1/fc fprop+dgrad+wgrad of %s, "
+                "%.2f GFLOP/image, %d image(s)/core x %d cores; pool/rnorm/elementwise (<0.1%% of CPU time) omitted; "
+                "slowest core %.1f s, wall %.1f s" % (what, flops_per_image(None) / 1e9, images_per_core, self.cores,
+                                                       max(per), wall))
+        return value, desc
+
+
+def measure(images_per_core=1, cores=None, full=True):
+    p = Pool(cores)
+    try:
+        value, desc = p.step(images_per_core, full)
+        return {"value": value, "unit": "images/s", "cores": p.cores, "kind": p.kind, "sample": desc}
+    finally:
+        p.close()
+
+
+if __name__ == "__main__":
+    print(measure(1, int(sys.argv[1]) if len(sys.argv) > 1 else None, full="--full" in sys.argv))
