@@ -114,7 +114,7 @@ __global__ void softmax_kernel(float* x, int rows, int cols) {
   float m = -INFINITY;
   for (int c = 0; c < cols; c++) m = fmaxf(m, x[n + (long long)rows * c]);
   float s = 0.f;
-  for (int c = 0; c < cols; c++) { const float e = __expf(x[n + (long long)rows * c] - m); x[n + (long long)rows * c] = e; s += e; }
+  for (int c = 0; c < cols; c++) { const float e = expf(x[n + (long long)rows * c] - m); x[n + (long long)rows * c] = e; s += e; }
   const float inv = 1.f / s;
   for (int c = 0; c < cols; c++) x[n + (long long)rows * c] *= inv;
 }
@@ -124,7 +124,7 @@ __global__ void softmax_ce_deriv_kernel(const float* __restrict__ p, const int* 
   if (n >= rows) return;
   const int lab = labels[n];
   for (int c = 0; c < cols; c++) deriv[n + (long long)rows * c] = p[n + (long long)rows * c] - (c == lab ? 1.f : 0.f);
-  if (loss) loss[n] = -__logf(fmaxf(p[n + (long long)rows * lab], 1e-30f));
+  if (loss) loss[n] = -logf(fmaxf(p[n + (long long)rows * lab], 1e-30f));
 }
 __global__ void sum_kernel(const float* __restrict__ a, float* out, int n) {   // single block
   float s = 0.f;

@@ -305,10 +305,22 @@ double ConvNet::FlopsTrainStep() const {
 }
 
 // =================================================================== GradChecker (src/grad_check.cc)
-float GradChecker::LossAt(Matrix& w, size_t index, float value) {
+float GradChecker::LossAt(Matrix& w, size_t index, float value) { return (float)LossAtD(w, index, value); }
+
+double GradChecker::LossAtD(Matrix& w, size_t index, float value) {
   w.WriteValue(index, value);
   Fprop(false);
-  return GetLoss();
+  // per-image cross-entropy on the device, summed in double on the host: the finite difference of two ~O(batch)
+  // losses must not lose the 1e-3-sized signal to fp32 summation noise
+  Layer& out = OutputLayer();
+  cnb_softmax_ce_deriv(out.GetState().GetDevData(), out.GetLabels(), out.GetDeriv().GetDevData(), out.GetLossPerImage(),
+                       batch_size_, out.GetState().GetCols());
+  std::vector<float> h(batch_size_);
+  HOST_CUDA_CHECK(cudaMemcpyAsync(h.data(), out.GetLossPerImage(), sizeof(float) * batch_size_, cudaMemcpyDeviceToHost, Matrix::Stream()));
+  HOST_CUDA_CHECK(cudaStreamSynchronize(Matrix::Stream()));
+  double s = 0;
+  for (float v : h) s += v;
+  return s;
 }
 
 std::vector<GradCheckResult> GradChecker::Run(unsigned seed) {
@@ -342,10 +354,10 @@ std::vector<GradCheckResult> GradChecker::Run(unsigned seed) {
       float diff_sum = 0; int non_zero = 0;
       for (int i = 0; i < n; i++) {
         const float val = w.ReadValue(i);
-        const float e1 = LossAt(w, i, val + epsilon);
-        const float e2 = LossAt(w, i, val - epsilon);
+        const double e1 = LossAtD(w, i, val + epsilon);
+        const double e2 = LossAtD(w, i, val - epsilon);
         w.WriteValue(i, val);
-        const float numeric = (e1 - e2) / (batch_size_ * 2 * epsilon);
+        const float numeric = (float)((e1 - e2) / (batch_size_ * 2.0 * epsilon));
         const float diff = analytical[i] - numeric, scale = (analytical[i] + numeric) / 2;
         if (!(scale == 0 && diff == 0)) { diff_sum += std::fabs(diff / scale); non_zero++; }
       }

@@ -148,6 +148,7 @@ class GradChecker : public ConvNet {
   std::vector<GradCheckResult> Run(unsigned seed);
  private:
   float LossAt(Matrix& w, size_t index, float value);
+  double LossAtD(Matrix& w, size_t index, float value);
 };
 
 // models.cc

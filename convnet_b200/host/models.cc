@@ -92,7 +92,7 @@ ModelConfig BuildTinyNet() {
   m.layer.back().is_output = true;
   EdgeConfig ap = E(AVGPOOL, 2, 2, 0);
   m.edge = {Conv(3, 1, 1), Pool(3, 2, 1), RNorm(0.01f, 0.75f, 0.5f), E(CONV_ONETOONE), Conv(3, 2, 1), ap, E(FC)};
-  for (EdgeConfig& e : m.edge) { e.grad_check = true; e.grad_check_num_params = 6; }
+  for (EdgeConfig& e : m.edge) { e.grad_check = true; e.grad_check_num_params = 8; e.grad_check_epsilon = {1e-2f, 3e-3f, 1e-3f}; }
   finish(m);
   return m;
 }

@@ -91,3 +91,69 @@ def test_c3d_video_net_step(env):
     assert math.isfinite(l0) and abs(l0 - math.log(101)) < 1.5
     assert torch.isfinite(n.grads_tensor()).all()
     n.close()
+
+
+def _torch_tiny_net(torch, n, batch):
+    """float64 PyTorch autograd model of models.cc BuildTinyNet(), sharing the native net's parameters."""
+    import torch.nn.functional as Fn
+    P = n.params_tensor().double()
+    edges = n.edges()
+    params = {}
+
+    def conv_w(i, cout, cin, k):
+        off, size = edges[i][2], edges[i][3]
+        K = cin * k * k
+        flat = P[off:off + size].clone()
+        w = flat[:cout * K].view(K, cout).view(cin, k, k, cout).permute(3, 0, 1, 2).contiguous().requires_grad_(True)
+        b = flat[cout * K:cout * K + cout].clone().requires_grad_(True)
+        params[i] = (w, b, K)
+        return w, b
+
+    x = n.input_tensor().double().view(8, 12, 12, batch).permute(3, 0, 1, 2).contiguous()       # [N, C, H, W]
+    labels = n.labels_tensor().long()
+    w0, b0 = conv_w(0, 16, 8, 3)
+    h = torch.relu(Fn.conv2d(x, w0, b0, stride=1, padding=1))
+    h = Fn.max_pool2d(h, 3, 2, 1)
+    # cross-map response norm, k = int(0.5 * 16) = 8, window [j - 4, j + 3] (gemm.cu:475-477)
+    k, a, bpow = 8, 0.01, 0.75
+    sq = Fn.pad(h * h, (0, 0, 0, 0, k // 2, k - k // 2 - 1))
+    S = sum(sq[:, j:j + 16] for j in range(k))
+    h = torch.relu(h * (1 + a * S) ** (-bpow))
+    w3, b3 = conv_w(3, 24, 16, 1)
+    h = torch.relu(Fn.conv2d(h, w3, b3))
+    w4, b4 = conv_w(4, 16, 24, 3)
+    h = torch.relu(Fn.conv2d(h, w4, b4, stride=2, padding=1))
+    h = Fn.avg_pool2d(h, 2, 2, 0)
+    w6, b6 = conv_w(6, 10, 16, 1)
+    logits = Fn.conv2d(h, w6, b6).flatten(1)
+    loss = Fn.cross_entropy(logits, labels, reduction="sum")
+    loss.backward()
+    return loss.item(), params
+
+
+def test_backprop_matches_float64_autograd(env):
+    """Every backward op of the chain (wgrad, dgrad, bias grad, max/avg-pool undo, response-norm undo, ReLU/softmax
+    derivatives) against an independent float64 PyTorch autograd model with the same parameters."""
+    torch, lib, net = env
+    for mode, tol in (("fp32", 2e-5), ("tf32", 2e-2)):
+        lib.set_precision(mode)
+        batch = 32
+        n = net.Net("tiny", batch, seed=7)
+        g = torch.Generator(device="cuda").manual_seed(11)
+        n.input_tensor().normal_(generator=g)
+        n.labels_tensor().copy_(torch.randint(0, 10, (batch,), device="cuda", generator=g, dtype=torch.int32))
+        n.fprop(False); n.bprop()
+        loss = n.loss()
+        ref_loss, params = _torch_tiny_net(torch, n, batch)
+        assert abs(loss - ref_loss) / ref_loss < (1e-5 if mode == "fp32" else 2e-3)
+        G = n.grads_tensor().double()
+        edges = n.edges()
+        for i, (w, b, K) in params.items():
+            off = edges[i][2]
+            cout = w.shape[0]
+            gw = G[off:off + cout * K].view(K, cout).view(w.shape[1], w.shape[2], w.shape[3], cout).permute(3, 0, 1, 2)
+            gb = G[off + cout * K:off + cout * K + cout]
+            for name, mine, ref in (("w", gw, w.grad / batch), ("b", gb, b.grad / batch)):   # scale_gradients / batch
+                err = ((mine - ref).abs().max() / ref.abs().mean().clamp_min(1e-12)).item()
+                assert err < tol, (mode, edges[i][0], name, err)
+        n.close()
