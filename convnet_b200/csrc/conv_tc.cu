@@ -46,6 +46,11 @@ struct TcParams {
   int BN, stages, tmem_cols;
   int m_tiles, n_tiles, num_tiles;
   int kc_blocks;                    // ceil(K-side channels / 32)
+  // "x mode" for tiny channel counts (Cin < 8, e.g. the RGB first layer): the kx taps of a filter row (padded to 8)
+  // take the place of the channel block.  fprop: one K block = (channel c, 4 filter rows) = 4x8 K rows;
+  // wgrad: the N tile is (x_ct channels) x (ky rows) x 8 taps, reduced over ALL modules at once.
+  int x_mode, x_yblocks, x_ct;
+  uint32_t b_tx_bytes;              // bytes the B-operand TMA(s) of one stage actually deliver
   int total_chunks;                 // fprop: nb*modules*frames ; dgrad: nb*W*H   (< 2^31, checked on the host)
   int splits, units_per_split;      // wgrad: (frame, module-row) units per reduction split
   float* out;
@@ -193,7 +198,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx_bytes = kAStageBytes + b_stage_bytes;
+      const uint32_t tx_bytes = kAStageBytes + p.b_tx_bytes;
       for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
         const Tile tile = decode_tile<OP>(p, t);
         auto begin_stage = [&]() -> uint8_t* {
@@ -211,6 +216,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             cX[c] = (ch.pos[c] % p.modX) * p.sx + p.px;
             cY[c] = (ch.pos[c] / p.modX) * p.sy + p.py;
           }
+          if (p.x_mode) {
+            for (int c = 0; c < p.Cin; c++)
+              for (int yb = 0; yb < p.x_yblocks; yb++) {
+                uint8_t* a = begin_stage();
+                uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
+#pragma unroll
+                for (int q = 0; q < 4; q++)      // 8 consecutive x pixels x 4 filter rows of channel c = 32 K rows
+                  ptx::tma_load_5d(&mapA, &ctl->full[stage], a + q * (BK * 128), ch.n[q], c, cX[q], cY[q] + 4 * yb, ch.f[q]);
+                for (int j = 0; j < p.BN / 32; j++)   // taps >= kx and rows >= ky are out of range -> zero weights
+                  ptx::tma_load_4d(&mapB, &ctl->full[stage], b + j * (BK * 128), tile.n_tile * p.BN + j * 32, 0, 4 * yb, c);
+                end_stage();
+              }
+          } else
           for (int ty = 0; ty < p.ky; ty++)
             for (int tx = 0; tx < p.kx; tx++) {
               const int tap = tx + p.kx * ty;
@@ -253,6 +271,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 end_stage();
               }
             }
+        } else if (p.x_mode) {
+          // reduction over every module of this split's rows; B holds x_ct channels x ky rows x 8 taps
+          const int r0 = tile.split * p.units_per_split, r1 = min(r0 + p.units_per_split, p.modY * p.frames);
+          const uint32_t c_bytes = (uint32_t)p.ky * 8 * 128;
+          for (int r = r0; r < r1; r++) {
+            const int f = r / p.modY, my = r % p.modY;
+            for (int mx = 0; mx < p.modX; mx++)
+              for (int ib = 0; ib < p.nb; ib++) {
+                uint8_t* a = begin_stage();
+                uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
+                ptx::tma_load_5d(&mapA, &ctl->full[stage], a, ib * 32, mx, my, tile.o_tile * BM, f);
+                for (int c = 0; c < p.x_ct; c++)
+                  ptx::tma_load_5d(&mapB, &ctl->full[stage], b + c * c_bytes, ib * 32, mx * p.sx + p.px, my * p.sy + p.py,
+                                   tile.c_tile * p.x_ct + c, f);
+                end_stage();
+              }
+          }
         } else {
           const WgradSpan sp = wgrad_span(p, tile);
           const int tx = tile.tap % p.kx, ty = tile.tap / p.kx;
@@ -302,10 +337,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const Tile tile = decode_tile<OP>(p, t);
       int nkb;
       if (OP == kFprop) {
-        nkb = p.taps * p.kc_blocks;
+        nkb = p.x_mode ? p.Cin * p.x_yblocks : p.taps * p.kc_blocks;
       } else if (OP == kDgrad) {
         const Chunks ch = decode_chunks(p, tile.m_tile, p.W * p.H);
         nkb = max(dgrad_live_taps(p, dgrad_taps(p, ch)), 1) * p.kc_blocks;
+      } else if (p.x_mode) {
+        const int r0 = tile.split * p.units_per_split, r1 = min(r0 + p.units_per_split, p.modY * p.frames);
+        nkb = (r1 - r0) * p.modX * p.nb;
       } else {
         const WgradSpan sp = wgrad_span(p, tile);
         nkb = max(sp.live_rows * (sp.mx_hi - sp.mx_lo + 1), 1) * p.nb;
@@ -357,6 +395,12 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         }
         ncols_valid = min(p.BN, (OP == kFprop ? p.Cout : p.Cin) - tile.n_tile * p.BN);
+      } else if (p.x_mode) {
+        // column j of the tile = tap tx + 8*(row ty + ky*channel): scattered to dW[o, tx + kx*(ty + ky*c)] below
+        const int o = tile.o_tile * BM + quarter * 32 + lane;
+        if (o < p.Cout) row_ptr = p.out + (long long)tile.split * p.Cout * p.taps * p.Cin + o;
+        ncols_valid = min(p.BN, p.x_ct * p.ky * 8);
+        direct_scale = (p.splits == 1);
       } else {
         const int o = tile.o_tile * BM + quarter * 32 + lane;
         const int c0 = tile.c_tile * p.BN;
@@ -378,6 +422,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int j = 0; j < 32; j++) {
             if (j0 + j < ncols_valid) {
               float* dst = row_ptr + col_stride * (j0 + j);
+              if (OP == kWgrad && p.x_mode) {
+                const int jg = j0 + j, tx = jg & 7, rr = jg >> 3, ty = rr % p.ky, c = tile.c_tile * p.x_ct + rr / p.ky;
+                if (tx >= p.kx || c >= p.Cin) continue;
+                dst = row_ptr + (long long)p.Cout * (tx + p.kx * (ty + p.ky * c));
+              }
               float r = v[j];
               if (direct_scale) r = (p.st == 0.f) ? p.so * r : p.st * (*dst) + p.so * r;
               *dst = r;
@@ -488,6 +537,7 @@ void fill_common(TcParams& p, const ConvGeom& g) {
   p.kx = g.kx; p.ky = g.ky; p.sx = g.sx; p.sy = g.sy; p.px = g.px; p.py = g.py; p.taps = g.kx * g.ky;
   p.frames = g.frames; p.frame0 = 0;
   p.splits = 1; p.units_per_split = 0;
+  p.x_mode = 0; p.x_yblocks = 0; p.x_ct = 0; p.b_tx_bytes = 0;
   p.out_frame_step = g.out_frame_step;
 }
 
@@ -512,10 +562,15 @@ bool image_map(CUtensorMap* m, const float* base, const ConvGeom& g, int Wd, int
 // ---- fprop ---------------------------------------------------------------------------------------
 bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, float* targets, float st, float so) {
   if (!tc_enabled() || !g.conv) return false;
-  if (g.N % 4 != 0 || g.Cout % 4 != 0 || g.Cin < 8) return false;          // TMA stride alignment / K efficiency
+  if (g.N % 4 != 0 || g.Cout % 4 != 0) return false;                        // TMA stride alignment
+  const bool x_mode = g.Cin < 8;                                            // tiny channel counts: taps take the K block
+  if (x_mode && (g.kx > 8 || g.ky > 8)) return false;
   TcParams p; fill_common(p, g);
   p.BN = pick_bn(g.Cout, 32);
   p.kc_blocks = ceil_div(g.Cin, BK);
+  p.x_mode = x_mode ? 1 : 0;
+  p.x_yblocks = ceil_div(g.ky, 4);
+  p.b_tx_bytes = (uint32_t)p.BN * BK * 4;
   const long long chunks = (long long)p.nb * g.modules * g.frames;
   if (chunks * 4 >= (1LL << 31)) return false;
   p.total_chunks = (int)chunks;
@@ -528,8 +583,18 @@ bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, fl
   CUtensorMap ma, mb;
   const float* img = images + (long long)g.cin0 * g.H * g.W * g.N;
   // frames of a 3-D conv start in_frame_step floats apart and see Cin (= Cin3d*kt) channels
-  if (!image_map(&ma, img, g, g.W, g.H, g.Cin, g.in_frame_step, true, BK)) return false;
-  {
+  if (x_mode) {
+    const long long N = g.N;
+    const long long adims[5] = {N, g.Cin, g.W, g.H, g.frames};
+    const long long astr[4] = {N * g.W * g.H, N, N * g.W, g.in_frame_step};
+    const int abox[5] = {32, 1, 8, 4, 1};                     // 8 x-taps x 4 filter rows of one channel
+    if (!make_map(&ma, img, 5, adims, astr, abox, true)) return false;
+    const long long bdims[4] = {g.Cout, g.kx, g.ky, g.Cin};
+    const long long bstr[3] = {g.Cout, (long long)g.Cout * g.kx, (long long)g.Cout * g.kx * g.ky};
+    const int bbox[4] = {32, 8, 4, 1};
+    if (!make_map(&mb, filters, 4, bdims, bstr, bbox, true)) return false;
+  } else {
+    if (!image_map(&ma, img, g, g.W, g.H, g.Cin, g.in_frame_step, true, BK)) return false;
     const long long dims[3] = {g.Cout, (long long)g.kx * g.ky, g.Cin};
     const long long str[2] = {g.Cout, (long long)g.Cout * g.kx * g.ky};
     const int box[3] = {32, 1, BK};
@@ -554,6 +619,7 @@ bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, 
   p.n_tiles = ceil_div(g.Cin, p.BN);
   p.num_tiles = p.m_tiles * p.n_tiles;
   p.so = so;
+  p.b_tx_bytes = (uint32_t)p.BN * BK * 4;
   p.idesc = ptx::make_idesc(2, true, false, BM, p.BN);
   CUtensorMap ma, mb;
   const float* der = derivs + (long long)g.cout0 * g.modules * g.N;
@@ -586,15 +652,26 @@ bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, 
 // ---- wgrad ---------------------------------------------------------------------------------------
 bool tc_conv_outp(const ConvGeom& g, const float* images, const float* derivs, float* targets, float st, float so) {
   if (!tc_enabled() || !g.conv) return false;
-  if (g.N % 4 != 0 || g.Cin < 8 || g.Cout < 8) return false;
+  if (g.N % 4 != 0 || g.Cout < 8) return false;
+  const bool x_mode = g.Cin < 8;
+  if (x_mode && (g.kx > 8 || g.ky > 8)) return false;
   TcParams p; fill_common(p, g);
-  p.BN = pick_bn(g.Cin, 16);
   p.kc_blocks = 0;
   p.total_chunks = 0;
   p.m_tiles = ceil_div(g.Cout, BM);
-  p.n_tiles = ceil_div(g.Cin, p.BN);
+  if (x_mode) {
+    p.x_mode = 1;
+    p.x_ct = std::min(g.Cin, 256 / (8 * g.ky));      // channels per N tile: x_ct * ky * 8 columns
+    p.BN = ceil_div(p.x_ct * g.ky * 8, 16) * 16;
+    p.n_tiles = ceil_div(g.Cin, p.x_ct);
+    p.b_tx_bytes = (uint32_t)p.x_ct * g.ky * 8 * 128;
+  } else {
+    p.BN = pick_bn(g.Cin, 16);
+    p.n_tiles = ceil_div(g.Cin, p.BN);
+    p.b_tx_bytes = (uint32_t)p.BN * BK * 4;
+  }
   const int units = g.modY * g.frames;               // reduction units = module rows
-  const long long base_tiles = (long long)p.taps * p.m_tiles * p.n_tiles;
+  const long long base_tiles = (long long)(x_mode ? 1 : p.taps) * p.m_tiles * p.n_tiles;
   int splits = (int)std::max<long long>(1, std::min<long long>(units, (2LL * num_sms()) / base_tiles));
   const long long elems = (long long)g.Cout * g.K;
   while (splits > 1 && elems * splits * 4 > (1LL << 30)) splits--;
@@ -607,7 +684,13 @@ bool tc_conv_outp(const ConvGeom& g, const float* images, const float* derivs, f
   const float* img = images + (long long)g.cin0 * g.H * g.W * g.N;
   const float* der = derivs + (long long)g.cout0 * g.modules * g.N;
   if (!image_map(&ma, der, g, g.modX, g.modY, g.Cout, g.out_frame_step, false, BM)) return false;
-  if (!image_map(&mb, img, g, g.W, g.H, g.Cin, g.in_frame_step, false, p.BN)) return false;
+  if (x_mode) {
+    const long long N = g.N;
+    const long long dims[5] = {N, g.W, g.H, g.Cin, g.frames};
+    const long long str[4] = {N, N * g.W, N * g.W * g.H, g.in_frame_step};
+    const int box[5] = {32, 8, g.ky, 1, 1};                   // 8 x-taps x ky rows of one channel: ky*8 GEMM columns
+    if (!make_map(&mb, img, 5, dims, str, box, false)) return false;
+  } else if (!image_map(&mb, img, g, g.W, g.H, g.Cin, g.in_frame_step, false, p.BN)) return false;
   if (p.splits == 1) {
     p.out = targets;
     launch<kWgrad>(ma, mb, p);

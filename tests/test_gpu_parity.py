@@ -138,6 +138,9 @@ CONV_CASES = {
     "ragged_batch": (37, 9, 8, 12, 20, 3, 2, 2, 1, 1, 0),         # N % 4 != 0, rectangular everything
     "single_image": (1, 6, 6, 4, 8, 3, 3, 1, 1, 1, 1),
     "batch_260": (260, 7, 7, 32, 64, 3, 3, 1, 1, 1, 1),           # N % 128 != 0, N % 4 == 0
+    "cin8_cout16": (32, 12, 12, 8, 16, 3, 3, 1, 1, 1, 1),         # one K block, mostly zero-filled
+    "cin24_s2": (32, 6, 6, 24, 16, 3, 3, 2, 2, 1, 1),
+    "cin16_1x1": (32, 6, 6, 16, 24, 1, 1, 1, 1, 0, 0),
 }
 
 
