@@ -360,6 +360,9 @@ std::vector<GradCheckResult> GradChecker::Run(unsigned seed) {
         const float numeric = (float)((e1 - e2) / (batch_size_ * 2.0 * epsilon));
         const float diff = analytical[i] - numeric, scale = (analytical[i] + numeric) / 2;
         if (!(scale == 0 && diff == 0)) { diff_sum += std::fabs(diff / scale); non_zero++; }
+        if (getenv("CNB_GRADCHECK_VERBOSE"))      // the reference prints this table (grad_check.cc:45-57)
+          printf("%s eps %g  analytical %.9f  numerical %.9f  diff %.3e  scaled %.3e\n", e->GetName().c_str(), epsilon,
+                 analytical[i], numeric, diff, scale != 0 ? std::fabs(diff / scale) : 0.f);
       }
       return non_zero ? diff_sum / non_zero : 0.f;
     };

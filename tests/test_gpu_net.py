@@ -22,12 +22,13 @@ def test_run_grad_check_passes_at_reference_tolerance(env):
     (conv, 1x1, fc behind pool / rnorm / avg-pool), in the exact-fp32 mode the check is specified for."""
     torch, lib, net = env
     lib.set_precision("fp32")
-    n = net.Net("gradcheck", 8, seed=3, grad_checker=True)
-    res = n.grad_check(seed=5)
-    n.close()
-    assert len(res) == 3
-    for name, eps, dw, db in res:
-        assert dw < 0.01 and db < 0.01, (name, eps, dw, db)
+    for seed in (1, 5, 9):
+        n = net.Net("gradcheck", 8, seed=3, grad_checker=True)
+        res = n.grad_check(seed=seed)
+        n.close()
+        assert len(res) == 3
+        for name, eps, dw, db in res:
+            assert dw < 0.01 and db < 0.01, (seed, res)
 
 
 def test_analytic_gradients_agree_between_fp32_and_tf32(env):
@@ -95,9 +96,21 @@ def test_c3d_video_net_step(env):
     n.close()
 
 
-def _torch_tiny_net(torch, n, batch):
-    """float64 PyTorch autograd model of models.cc BuildTinyNet(), sharing the native net's parameters."""
+# float64 PyTorch autograd mirrors of models.cc nets, sharing the native net's parameters.
+# spec entries: ("conv", cout, k, stride, pad, relu) | ("maxpool", k, s, p) | ("avgpool", k, s, p) |
+#               ("rnorm", k, alpha, beta, relu) | ("fc", cout)
+TORCH_NETS = {
+    "tiny": dict(cin=8, size=12, spec=[("conv", 16, 3, 1, 1, True), ("maxpool", 3, 2, 1), ("rnorm", 8, 0.01, 0.75, True),
+                                      ("conv", 24, 1, 1, 0, True), ("conv", 16, 3, 2, 1, True), ("avgpool", 2, 2, 0),
+                                      ("fc", 10)]),
+    "gradcheck": dict(cin=4, size=8, spec=[("conv", 8, 3, 1, 1, False), ("avgpool", 3, 2, 1), ("rnorm", 4, 0.01, 0.75, False),
+                                          ("conv", 12, 1, 1, 0, False), ("fc", 5)]),
+}
+
+
+def _torch_net(torch, n, batch, model):
     import torch.nn.functional as Fn
+    cfg = TORCH_NETS[model]
     P = n.params_tensor().double()
     edges = n.edges()
     params = {}
@@ -111,49 +124,64 @@ def _torch_tiny_net(torch, n, batch):
         params[i] = (w, b, K)
         return w, b
 
-    x = n.input_tensor().double().view(8, 12, 12, batch).permute(3, 0, 1, 2).contiguous()       # [N, C, H, W]
+    C, S = cfg["cin"], cfg["size"]
+    h = n.input_tensor().double().view(C, S, S, batch).permute(3, 0, 1, 2).contiguous()       # [N, C, H, W]
     labels = n.labels_tensor().long()
-    w0, b0 = conv_w(0, 16, 8, 3)
-    h = torch.relu(Fn.conv2d(x, w0, b0, stride=1, padding=1))
-    h = Fn.max_pool2d(h, 3, 2, 1)
-    # cross-map response norm, k = int(0.5 * 16) = 8, window [j - 4, j + 3] (gemm.cu:475-477)
-    k, a, bpow = 8, 0.01, 0.75
-    sq = Fn.pad(h * h, (0, 0, 0, 0, k // 2, k - k // 2 - 1))
-    S = sum(sq[:, j:j + 16] for j in range(k))
-    h = torch.relu(h * (1 + a * S) ** (-bpow))
-    w3, b3 = conv_w(3, 24, 16, 1)
-    h = torch.relu(Fn.conv2d(h, w3, b3))
-    w4, b4 = conv_w(4, 16, 24, 3)
-    h = torch.relu(Fn.conv2d(h, w4, b4, stride=2, padding=1))
-    h = Fn.avg_pool2d(h, 2, 2, 0)
-    w6, b6 = conv_w(6, 10, 16, 1)
-    logits = Fn.conv2d(h, w6, b6).flatten(1)
-    loss = Fn.cross_entropy(logits, labels, reduction="sum")
+    for i, e in enumerate(cfg["spec"]):
+        if e[0] == "conv":
+            _, cout, k, s, p, relu = e
+            w, b = conv_w(i, cout, h.shape[1], k)
+            h = Fn.conv2d(h, w, b, stride=s, padding=p)
+            h = torch.relu(h) if relu else h
+        elif e[0] == "maxpool":
+            h = Fn.max_pool2d(h, e[1], e[2], e[3])
+        elif e[0] == "avgpool":
+            h = Fn.avg_pool2d(h, e[1], e[2], e[3], count_include_pad=False)
+        elif e[0] == "rnorm":                                  # window [j - k/2, j - k/2 + k) (gemm.cu:475-477)
+            _, k, a, bpow, relu = e
+            F_ = h.shape[1]
+            sq = Fn.pad(h * h, (0, 0, 0, 0, k // 2, k - k // 2 - 1))
+            Ssum = sum(sq[:, j:j + F_] for j in range(k))
+            h = h * (1 + a * Ssum) ** (-bpow)
+            h = torch.relu(h) if relu else h
+        elif e[0] == "fc":                                     # features flattened as x + W*(y + H*c)
+            cout = e[1]
+            K = h.shape[1] * h.shape[2] * h.shape[3]
+            off, size = edges[i][2], edges[i][3]
+            flat = P[off:off + size].clone()
+            w = flat[:cout * K].view(K, cout).clone().requires_grad_(True)           # [K, cout], K = (c, y, x)
+            b = flat[cout * K:cout * K + cout].clone().requires_grad_(True)
+            params[i] = (w, b, K)
+            h = h.reshape(batch, K) @ w + b
+    loss = Fn.cross_entropy(h, labels, reduction="sum")
     loss.backward()
     return loss.item(), params
 
 
-def test_backprop_matches_float64_autograd(env):
+@pytest.mark.parametrize("model", sorted(TORCH_NETS))
+def test_backprop_matches_float64_autograd(env, model):
     """Every backward op of the chain (wgrad, dgrad, bias grad, max/avg-pool undo, response-norm undo, ReLU/softmax
     derivatives) against an independent float64 PyTorch autograd model with the same parameters."""
     torch, lib, net = env
     for mode, tol in (("fp32", 2e-5), ("tf32", 5e-2)):
         lib.set_precision(mode)
         batch = 32
-        n = net.Net("tiny", batch, seed=7)
+        n = net.Net(model, batch, seed=7)
         g = torch.Generator(device="cuda").manual_seed(11)
         n.input_tensor().normal_(generator=g)
-        n.labels_tensor().copy_(torch.randint(0, 10, (batch,), device="cuda", generator=g, dtype=torch.int32))
+        n.labels_tensor().copy_(torch.randint(0, n.num_classes, (batch,), device="cuda", generator=g, dtype=torch.int32))
         n.fprop(False); n.bprop()
         loss = n.loss()
-        ref_loss, params = _torch_tiny_net(torch, n, batch)
+        ref_loss, params = _torch_net(torch, n, batch, model)
         assert abs(loss - ref_loss) / ref_loss < (1e-5 if mode == "fp32" else 2e-3)
         G = n.grads_tensor().double()
         edges = n.edges()
         for i, (w, b, K) in params.items():
             off = edges[i][2]
-            cout = w.shape[0]
-            gw = G[off:off + cout * K].view(K, cout).view(w.shape[1], w.shape[2], w.shape[3], cout).permute(3, 0, 1, 2)
+            cout = b.shape[0]
+            gw = G[off:off + cout * K].view(K, cout)
+            if w.dim() == 4:
+                gw = gw.view(w.shape[1], w.shape[2], w.shape[3], cout).permute(3, 0, 1, 2)
             gb = G[off + cout * K:off + cout * K + cout]
             for name, mine, ref in (("w", gw, w.grad / batch), ("b", gb, b.grad / batch)):   # scale_gradients / batch
                 if mode == "fp32":      # exact arithmetic: every entry matches
