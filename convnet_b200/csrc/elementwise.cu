@@ -106,17 +106,27 @@ __global__ void mult_kernel(float* a, const float* __restrict__ b, long long n) 
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] *= b[i];
 }
 
-// softmax over classes of a column-major [rows x cols] matrix: one thread per image, reads strided by rows
-// (coalesced across images); three passes over <= a few thousand classes.
-__global__ void softmax_kernel(float* x, int rows, int cols) {
-  const int n = blockIdx.x * blockDim.x + threadIdx.x;
-  if (n >= rows) return;
+// softmax over classes of a column-major [rows x cols] matrix: one block per 32 images; lane = image (coalesced
+// along rows), the block's warps split the classes; max and sum combined through shared memory.
+__global__ void __launch_bounds__(256) softmax_kernel(float* x, int rows, int cols) {
+  __shared__ float red[8][33];
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int n = blockIdx.x * 32 + lane;
+  const bool ok = n < rows;
   float m = -INFINITY;
-  for (int c = 0; c < cols; c++) m = fmaxf(m, x[n + (long long)rows * c]);
+  if (ok) for (int c = w; c < cols; c += 8) m = fmaxf(m, x[n + (long long)rows * c]);
+  red[w][lane] = m;
+  __syncthreads();
+  for (int k = 0; k < 8; k++) m = fmaxf(m, red[k][lane]);
+  __syncthreads();
   float s = 0.f;
-  for (int c = 0; c < cols; c++) { const float e = expf(x[n + (long long)rows * c] - m); x[n + (long long)rows * c] = e; s += e; }
+  if (ok) for (int c = w; c < cols; c += 8) { const float e = expf(x[n + (long long)rows * c] - m); x[n + (long long)rows * c] = e; s += e; }
+  red[w][lane] = s;
+  __syncthreads();
+  s = 0.f;
+  for (int k = 0; k < 8; k++) s += red[k][lane];
   const float inv = 1.f / s;
-  for (int c = 0; c < cols; c++) x[n + (long long)rows * c] *= inv;
+  if (ok) for (int c = w; c < cols; c += 8) x[n + (long long)rows * c] *= inv;
 }
 __global__ void softmax_ce_deriv_kernel(const float* __restrict__ p, const int* __restrict__ labels, float* deriv,
                                         float* loss, int rows, int cols) {
@@ -184,7 +194,7 @@ void cnb_mult(float* a, const float* b, long long n) {
 }
 void cnb_softmax(float* x, int rows, int cols) {
   if (rows <= 0) return;
-  softmax_kernel<<<ceil_div(rows, 128), 128, 0, state().stream>>>(x, rows, cols);
+  softmax_kernel<<<ceil_div(rows, 32), 256, 0, state().stream>>>(x, rows, cols);
   count_launch(); CNB_LAUNCH_CHECK("softmax");
 }
 void cnb_softmax_ce_deriv(const float* probs, const int* labels, float* deriv, float* loss_per_image, int rows, int cols) {
