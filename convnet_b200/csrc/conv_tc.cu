@@ -51,6 +51,9 @@ struct TcParams {
   // wgrad: the N tile is (x_ct channels) x (ky rows) x 8 taps, reduced over ALL modules at once.
   int x_mode, x_yblocks, x_ct;
   uint32_t b_tx_bytes;              // bytes the B-operand TMA(s) of one stage actually deliver
+  // merged requests: when N % 128 == 0 (2-D) the four 32-image chunks of an m-tile are one box over a
+  // (32, ..., N/32, ...) view of the tensor; when Cout % 32 == 0 the BN/32 filter chunks are one box likewise.
+  int a_merged, b_merged;
   int total_chunks;                 // fprop: nb*modules*frames ; dgrad: nb*W*H   (< 2^31, checked on the host)
   int splits, units_per_split;      // wgrad: (frame, module-row) units per reduction split
   float* out;
@@ -221,11 +224,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               for (int yb = 0; yb < p.x_yblocks; yb++) {
                 uint8_t* a = begin_stage();
                 uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
+                if (p.a_merged) {                // dims (n_lo, x, y, n_hi, c): one 16 KiB request
+                  ptx::tma_load_5d(&mapA, &ctl->full[stage], a, 0, cX[0], cY[0] + 4 * yb, ch.n[0] >> 5, c);
+                } else {
 #pragma unroll
-                for (int q = 0; q < 4; q++)      // 8 consecutive x pixels x 4 filter rows of channel c = 32 K rows
-                  ptx::tma_load_5d(&mapA, &ctl->full[stage], a + q * (BK * 128), ch.n[q], c, cX[q], cY[q] + 4 * yb, ch.f[q]);
-                for (int j = 0; j < p.BN / 32; j++)   // taps >= kx and rows >= ky are out of range -> zero weights
-                  ptx::tma_load_4d(&mapB, &ctl->full[stage], b + j * (BK * 128), tile.n_tile * p.BN + j * 32, 0, 4 * yb, c);
+                  for (int q = 0; q < 4; q++)    // 8 consecutive x pixels x 4 filter rows of channel c = 32 K rows
+                    ptx::tma_load_5d(&mapA, &ctl->full[stage], a + q * (BK * 128), ch.n[q], c, cX[q], cY[q] + 4 * yb, ch.f[q]);
+                }
+                if (p.b_merged) {                // dims (o_lo, tx, ty, o_hi, c)
+                  ptx::tma_load_5d(&mapB, &ctl->full[stage], b, 0, 0, 4 * yb, tile.n_tile * (p.BN >> 5), c);
+                } else {
+                  for (int j = 0; j < p.BN / 32; j++)   // taps >= kx and rows >= ky are out of range -> zero weights
+                    ptx::tma_load_4d(&mapB, &ctl->full[stage], b + j * (BK * 128), tile.n_tile * p.BN + j * 32, 0, 4 * yb, c);
+                }
                 end_stage();
               }
           } else
@@ -235,11 +246,19 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               for (int cb = 0; cb < p.kc_blocks; cb++) {
                 uint8_t* a = begin_stage();
                 uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
+                if (p.a_merged) {                // dims (n_lo, c, n_hi, x, y): one 16 KiB request
+                  ptx::tma_load_5d(&mapA, &ctl->full[stage], a, 0, cb * BK, ch.n[0] >> 5, cX[0] + tx, cY[0] + ty);
+                } else {
 #pragma unroll
-                for (int c = 0; c < 4; c++)
-                  ptx::tma_load_5d(&mapA, &ctl->full[stage], a + c * (BK * 128), ch.n[c], cb * BK, cX[c] + tx, cY[c] + ty, ch.f[c]);
-                for (int j = 0; j < p.BN / 32; j++)
-                  ptx::tma_load_3d(&mapB, &ctl->full[stage], b + j * (BK * 128), tile.n_tile * p.BN + j * 32, tap, cb * BK);
+                  for (int c = 0; c < 4; c++)
+                    ptx::tma_load_5d(&mapA, &ctl->full[stage], a + c * (BK * 128), ch.n[c], cb * BK, cX[c] + tx, cY[c] + ty, ch.f[c]);
+                }
+                if (p.b_merged) {                // dims (o_lo, c, o_hi, tap)
+                  ptx::tma_load_4d(&mapB, &ctl->full[stage], b, 0, cb * BK, tile.n_tile * (p.BN >> 5), tap);
+                } else {
+                  for (int j = 0; j < p.BN / 32; j++)
+                    ptx::tma_load_3d(&mapB, &ctl->full[stage], b + j * (BK * 128), tile.n_tile * p.BN + j * 32, tap, cb * BK);
+                }
                 end_stage();
               }
             }
@@ -264,9 +283,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               for (int ob = 0; ob < p.kc_blocks; ob++) {
                 uint8_t* a = begin_stage();
                 uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
+                if (p.a_merged) {                // all four chunks sit on the same pixel: dims (n_lo, o, n_hi, mx, my)
+                  ptx::tma_load_5d(&mapA, &ctl->full[stage], a, 0, ob * BK, ch.n[0] >> 5, mx[0], my[0]);
+                } else {
 #pragma unroll
-                for (int c = 0; c < 4; c++)
-                  ptx::tma_load_5d(&mapA, &ctl->full[stage], a + c * (BK * 128), ch.n[c], ob * BK, mx[c], my[c], p.frame0);
+                  for (int c = 0; c < 4; c++)
+                    ptx::tma_load_5d(&mapA, &ctl->full[stage], a + c * (BK * 128), ch.n[c], ob * BK, mx[c], my[c], p.frame0);
+                }
                 ptx::tma_load_3d(&mapB, &ctl->full[stage], b, ob * BK, tap, tile.n_tile * p.BN);
                 end_stage();
               }
@@ -538,6 +561,7 @@ void fill_common(TcParams& p, const ConvGeom& g) {
   p.frames = g.frames; p.frame0 = 0;
   p.splits = 1; p.units_per_split = 0;
   p.x_mode = 0; p.x_yblocks = 0; p.x_ct = 0; p.b_tx_bytes = 0;
+  p.a_merged = 0; p.b_merged = 0;
   p.out_frame_step = g.out_frame_step;
 }
 
@@ -555,6 +579,21 @@ bool image_map(CUtensorMap* m, const float* base, const ConvGeom& g, int Wd, int
   const long long str[4] = {N, N * Wd, N * Wd * Hd, frame_step};
   const int box[5] = {32, 1, 1, box_c, 1};
   return make_map(m, base, 5, dims, str, box, false);
+}
+
+// (n_lo = 32, channel / x / y ..., n_hi = N/32) view for one-request A tiles; `x_mode`: box {32, 8x, 4y, 4 n_hi, 1c}
+bool merged_image_map(CUtensorMap* m, const float* base, const ConvGeom& g, int Wd, int Hd, int C, bool x_mode) {
+  const long long N = g.N;
+  if (x_mode) {
+    const long long dims[5] = {32, Wd, Hd, N / 32, C};
+    const long long str[4] = {N, N * Wd, 32, N * Wd * Hd};
+    const int box[5] = {32, 8, 4, 4, 1};
+    return make_map(m, base, 5, dims, str, box, true);
+  }
+  const long long dims[5] = {32, C, N / 32, Wd, Hd};
+  const long long str[4] = {N * Wd * Hd, 32, N, N * Wd};
+  const int box[5] = {32, BK, 4, 1, 1};
+  return make_map(m, base, 5, dims, str, box, true);
 }
 
 }  // namespace
@@ -582,23 +621,47 @@ bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, fl
   p.idesc = ptx::make_idesc(2, true, true, BM, p.BN);
   CUtensorMap ma, mb;
   const float* img = images + (long long)g.cin0 * g.H * g.W * g.N;
+  static const bool allow_merge = !(getenv("CONVNET_B200_NO_TMA_MERGE") && getenv("CONVNET_B200_NO_TMA_MERGE")[0] == '1');
+  p.a_merged = (allow_merge && g.frames == 1 && g.N % 128 == 0) ? 1 : 0;
+  p.b_merged = (allow_merge && g.Cout % 32 == 0) ? 1 : 0;
+  const long long taps = (long long)g.kx * g.ky;
   // frames of a 3-D conv start in_frame_step floats apart and see Cin (= Cin3d*kt) channels
   if (x_mode) {
     const long long N = g.N;
-    const long long adims[5] = {N, g.Cin, g.W, g.H, g.frames};
-    const long long astr[4] = {N * g.W * g.H, N, N * g.W, g.in_frame_step};
-    const int abox[5] = {32, 1, 8, 4, 1};                     // 8 x-taps x 4 filter rows of one channel
-    if (!make_map(&ma, img, 5, adims, astr, abox, true)) return false;
-    const long long bdims[4] = {g.Cout, g.kx, g.ky, g.Cin};
-    const long long bstr[3] = {g.Cout, (long long)g.Cout * g.kx, (long long)g.Cout * g.kx * g.ky};
-    const int bbox[4] = {32, 8, 4, 1};
-    if (!make_map(&mb, filters, 4, bdims, bstr, bbox, true)) return false;
+    if (p.a_merged) {
+      if (!merged_image_map(&ma, img, g, g.W, g.H, g.Cin, true)) return false;
+    } else {
+      const long long adims[5] = {N, g.Cin, g.W, g.H, g.frames};
+      const long long astr[4] = {N * g.W * g.H, N, N * g.W, g.in_frame_step};
+      const int abox[5] = {32, 1, 8, 4, 1};                     // 8 x-taps x 4 filter rows of one channel
+      if (!make_map(&ma, img, 5, adims, astr, abox, true)) return false;
+    }
+    if (p.b_merged) {
+      const long long bdims[5] = {32, g.kx, g.ky, g.Cout / 32, g.Cin};
+      const long long bstr[4] = {g.Cout, (long long)g.Cout * g.kx, 32, (long long)g.Cout * taps};
+      const int bbox[5] = {32, 8, 4, p.BN / 32, 1};
+      if (!make_map(&mb, filters, 5, bdims, bstr, bbox, true)) return false;
+    } else {
+      const long long bdims[4] = {g.Cout, g.kx, g.ky, g.Cin};
+      const long long bstr[3] = {g.Cout, (long long)g.Cout * g.kx, (long long)g.Cout * taps};
+      const int bbox[4] = {32, 8, 4, 1};
+      if (!make_map(&mb, filters, 4, bdims, bstr, bbox, true)) return false;
+    }
   } else {
-    if (!image_map(&ma, img, g, g.W, g.H, g.Cin, g.in_frame_step, true, BK)) return false;
-    const long long dims[3] = {g.Cout, (long long)g.kx * g.ky, g.Cin};
-    const long long str[2] = {g.Cout, (long long)g.Cout * g.kx * g.ky};
-    const int box[3] = {32, 1, BK};
-    if (!make_map(&mb, filters, 3, dims, str, box, true)) return false;
+    if (p.a_merged) {
+      if (!merged_image_map(&ma, img, g, g.W, g.H, g.Cin, false)) return false;
+    } else if (!image_map(&ma, img, g, g.W, g.H, g.Cin, g.in_frame_step, true, BK)) return false;
+    if (p.b_merged) {
+      const long long dims[4] = {32, g.Cin, g.Cout / 32, taps};
+      const long long str[3] = {(long long)g.Cout * taps, 32, g.Cout};
+      const int box[4] = {32, BK, p.BN / 32, 1};
+      if (!make_map(&mb, filters, 4, dims, str, box, true)) return false;
+    } else {
+      const long long dims[3] = {g.Cout, taps, g.Cin};
+      const long long str[2] = {g.Cout, (long long)g.Cout * taps};
+      const int box[3] = {32, 1, BK};
+      if (!make_map(&mb, filters, 3, dims, str, box, true)) return false;
+    }
   }
   launch<kFprop>(ma, mb, p);
   state().last_conv_path = kPathTcTf32;
@@ -623,7 +686,11 @@ bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, 
   p.idesc = ptx::make_idesc(2, true, false, BM, p.BN);
   CUtensorMap ma, mb;
   const float* der = derivs + (long long)g.cout0 * g.modules * g.N;
-  if (!image_map(&ma, der, g, g.modX, g.modY, g.Cout, g.out_frame_step, true, BK)) return false;
+  static const bool allow_merge = !(getenv("CONVNET_B200_NO_TMA_MERGE") && getenv("CONVNET_B200_NO_TMA_MERGE")[0] == '1');
+  p.a_merged = (allow_merge && g.frames == 1 && g.N % 128 == 0) ? 1 : 0;
+  if (p.a_merged) {
+    if (!merged_image_map(&ma, der, g, g.modX, g.modY, g.Cout, false)) return false;
+  } else if (!image_map(&ma, der, g, g.modX, g.modY, g.Cout, g.out_frame_step, true, BK)) return false;
   {
     const long long dims[3] = {g.Cout, (long long)g.kx * g.ky, g.Cin};
     const long long str[2] = {g.Cout, (long long)g.Cout * g.kx * g.ky};
