@@ -29,7 +29,9 @@ template <> __device__ __forceinline__ void vstore<4>(float* p, const float (&v)
 template <> __device__ __forceinline__ void vstore<1>(float* p, const float (&v)[1]) { *p = v[0]; }
 
 // ---- forward -------------------------------------------------------------------------
-template <int VEC, bool MAX>
+// K > 0: 2-D window with kx, ky <= K, fully unrolled with predicated loads so that all K*K 16-byte loads of a
+// thread are in flight together (the generic K == 0 version walks the window with runtime loops, one load at a time).
+template <int VEC, bool MAX, int K>
 __global__ void __launch_bounds__(256) pool_fwd_kernel(PoolGeom g, const float* __restrict__ images,
                                                         float* __restrict__ targets, float so, long long total) {
   const int NV = g.N / VEC;
@@ -41,24 +43,47 @@ __global__ void __launch_bounds__(256) pool_fwd_kernel(PoolGeom g, const float* 
     const int my = (int)(r % g.modY); r /= g.modY;
     const int c = (int)(r % g.C);
     const int mt = (int)(r / g.C);
-    int sX = mx * g.sx + g.px, sY = my * g.sy + g.py, sT = mt * g.st + g.pt;
-    const int eX = min(sX + g.kx, g.W), eY = min(sY + g.ky, g.H), eT = min(sT + g.kt, g.T);
-    sX = max(sX, 0); sY = max(sY, 0); sT = max(sT, 0);
     float acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; v++) acc[v] = MAX ? -2e38f : 0.f;     // base value: gemm.cu:71
-    for (int T = sT; T < eT; T++)
-      for (int Y = sY; Y < eY; Y++) {
-        const float* row = images + (long long)g.N * ((long long)g.W * (Y + (long long)g.H * (c + (long long)g.C * T))) + nv * VEC;
-        for (int X = sX; X < eX; X++) {
-          float a[VEC];
-          vload<VEC>(row + (long long)g.N * X, a);
+    int region = 0;
+    if constexpr (K > 0) {
+      const int X0 = mx * g.sx + g.px, Y0 = my * g.sy + g.py;
+      const float* base = images + (long long)g.N * ((long long)g.W * g.H * (c + (long long)g.C * mt)) + nv * VEC;
+      float a[K * K][VEC];
+      bool ok[K * K];
 #pragma unroll
-          for (int v = 0; v < VEC; v++) acc[v] = MAX ? fmaxf(acc[v], a[v]) : acc[v] + a[v];
+      for (int dy = 0; dy < K; dy++)
+#pragma unroll
+        for (int dx = 0; dx < K; dx++) {
+          const int X = X0 + dx, Y = Y0 + dy;
+          ok[dy * K + dx] = dy < g.ky && dx < g.kx && (unsigned)X < (unsigned)g.W && (unsigned)Y < (unsigned)g.H;
+          if (ok[dy * K + dx]) vload<VEC>(base + (long long)g.N * (X + (long long)g.W * Y), a[dy * K + dx]);
         }
-      }
+#pragma unroll
+      for (int t = 0; t < K * K; t++)
+        if (ok[t]) {
+          region++;
+#pragma unroll
+          for (int v = 0; v < VEC; v++) acc[v] = MAX ? fmaxf(acc[v], a[t][v]) : acc[v] + a[t][v];
+        }
+    } else {
+      int sX = mx * g.sx + g.px, sY = my * g.sy + g.py, sT = mt * g.st + g.pt;
+      const int eX = min(sX + g.kx, g.W), eY = min(sY + g.ky, g.H), eT = min(sT + g.kt, g.T);
+      sX = max(sX, 0); sY = max(sY, 0); sT = max(sT, 0);
+      for (int T = sT; T < eT; T++)
+        for (int Y = sY; Y < eY; Y++) {
+          const float* row = images + (long long)g.N * ((long long)g.W * (Y + (long long)g.H * (c + (long long)g.C * T))) + nv * VEC;
+          for (int X = sX; X < eX; X++) {
+            float a[VEC];
+            vload<VEC>(row + (long long)g.N * X, a);
+#pragma unroll
+            for (int v = 0; v < VEC; v++) acc[v] = MAX ? fmaxf(acc[v], a[v]) : acc[v] + a[v];
+          }
+        }
+      region = (eX - sX) * (eY - sY) * (eT - sT);                  // CLIPPED count: gemm.cu:185
+    }
     if (!MAX) {
-      const int region = (eX - sX) * (eY - sY) * (eT - sT);        // CLIPPED count: gemm.cu:185
 #pragma unroll
       for (int v = 0; v < VEC; v++) acc[v] = acc[v] / region;
     }
@@ -77,7 +102,9 @@ __device__ __forceinline__ void cover(int X, int s, int p, int k, int mods, int&
   hi = b < 0 ? -1 : min(b / s, mods - 1);
 }
 
-template <int VEC, bool MAX>
+// Q > 0: 2-D pooling where at most Q windows cover an element along each axis (kernel <= Q*stride): the Q*Q window
+// visits are unrolled and predicated so their loads overlap; Q == 0 is the generic (3-D, any geometry) version.
+template <int VEC, bool MAX, int Q>
 __global__ void __launch_bounds__(256) pool_undo_kernel(PoolGeom g, const float* __restrict__ images,
                                                          const float* __restrict__ grads,
                                                          const float* __restrict__ acts, float* targets,
@@ -95,36 +122,57 @@ __global__ void __launch_bounds__(256) pool_undo_kernel(PoolGeom g, const float*
     cover(X, g.sx, g.px, g.kx, g.modX, x0, x1);
     cover(Y, g.sy, g.py, g.ky, g.modY, y0, y1);
     cover(T, g.st, g.pt, g.kt, g.modT, t0, t1);
-    float img[VEC], acc[VEC];
+    float img[VEC], acc[VEC], old[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; v++) acc[v] = 0.f;
+    for (int v = 0; v < VEC; v++) { acc[v] = 0.f; old[v] = 0.f; img[v] = 0.f; }
     if (MAX) vload<VEC>(images + idx * VEC, img);
-    for (int mt = t0; mt <= t1; mt++)
-      for (int my = y0; my <= y1; my++)
-        for (int mx = x0; mx <= x1; mx++) {
-          const long long off = (long long)g.N * (mx + (long long)g.modX * (my + (long long)g.modY * (c + (long long)g.C * mt))) + nv * VEC;
-          float gr[VEC];
-          vload<VEC>(grads + off, gr);
-          if (MAX) {
-            float a[VEC];
-            vload<VEC>(acts + off, a);
+    if (st != 0.f) vload<VEC>(targets + idx * VEC, old);
+    auto visit = [&](int mx, int my, int mt, const float (&gr)[VEC], const float (&a)[VEC]) {
+      if (MAX) {
 #pragma unroll
-            for (int v = 0; v < VEC; v++) acc[v] += (img[v] == a[v]) ? so * gr[v] : 0.f;   // ties duplicate: gemm.cu:291
-          } else {
-            int sX = mx * g.sx + g.px, sY = my * g.sy + g.py, sT = mt * g.st + g.pt;
-            const int eX = min(sX + g.kx, g.W), eY = min(sY + g.ky, g.H), eT = min(sT + g.kt, g.T);
-            sX = max(sX, 0); sY = max(sY, 0); sT = max(sT, 0);
-            const int region = (eX - sX) * (eY - sY) * (eT - sT);
+        for (int v = 0; v < VEC; v++) acc[v] += (img[v] == a[v]) ? so * gr[v] : 0.f;     // ties duplicate: gemm.cu:291
+      } else {
+        int sX = mx * g.sx + g.px, sY = my * g.sy + g.py, sT = mt * g.st + g.pt;
+        const int eX = min(sX + g.kx, g.W), eY = min(sY + g.ky, g.H), eT = min(sT + g.kt, g.T);
+        sX = max(sX, 0); sY = max(sY, 0); sT = max(sT, 0);
+        const int region = (eX - sX) * (eY - sY) * (eT - sT);
 #pragma unroll
-            for (int v = 0; v < VEC; v++) acc[v] += so * gr[v] / region;                  // gemm.cu:237
+        for (int v = 0; v < VEC; v++) acc[v] += so * gr[v] / region;                      // gemm.cu:237
+      }
+    };
+    if constexpr (Q > 0) {
+      float gr[Q * Q][VEC], a[Q * Q][VEC];
+      bool ok[Q * Q];
+#pragma unroll
+      for (int j = 0; j < Q; j++)
+#pragma unroll
+        for (int i = 0; i < Q; i++) {
+          const int mx = x0 + i, my = y0 + j;
+          ok[j * Q + i] = mx <= x1 && my <= y1;
+          if (ok[j * Q + i]) {
+            const long long off = (long long)g.N * (mx + (long long)g.modX * (my + (long long)g.modY * (c + (long long)g.C * t0))) + nv * VEC;
+            vload<VEC>(grads + off, gr[j * Q + i]);
+            if (MAX) vload<VEC>(acts + off, a[j * Q + i]);
           }
         }
-    if (st != 0.f) {
-      float t[VEC];
-      vload<VEC>(targets + idx * VEC, t);
 #pragma unroll
-      for (int v = 0; v < VEC; v++) acc[v] += st * t[v];
+      for (int j = 0; j < Q; j++)
+#pragma unroll
+        for (int i = 0; i < Q; i++)
+          if (ok[j * Q + i]) visit(x0 + i, y0 + j, t0, gr[j * Q + i], a[j * Q + i]);
+    } else {
+      for (int mt = t0; mt <= t1; mt++)
+        for (int my = y0; my <= y1; my++)
+          for (int mx = x0; mx <= x1; mx++) {
+            const long long off = (long long)g.N * (mx + (long long)g.modX * (my + (long long)g.modY * (c + (long long)g.C * mt))) + nv * VEC;
+            float gr[VEC], a[VEC];
+            vload<VEC>(grads + off, gr);
+            if (MAX) vload<VEC>(acts + off, a); else { for (int v = 0; v < VEC; v++) a[v] = 0.f; }
+            visit(mx, my, mt, gr, a);
+          }
     }
+#pragma unroll
+    for (int v = 0; v < VEC; v++) acc[v] += st * old[v];
     vstore<VEC>(targets + idx * VEC, acc);
   }
 }
@@ -136,21 +184,41 @@ static int grid_for(long long total) {
   return (int)std::min<long long>(want, (long long)num_sms() * 16);   // multiple of the SM count when large
 }
 
+template <int VEC, bool MAX>
+static void launch_fwd(const PoolGeom& g, const float* images, float* targets, float so, long long total) {
+  cudaStream_t s = state().stream;
+  const int grid = grid_for(total);
+  const int k = (g.kt == 1 && g.T == 1 && g.modT == 1) ? std::max(g.kx, g.ky) : 99;
+  if (k <= 2) pool_fwd_kernel<VEC, MAX, 2><<<grid, 256, 0, s>>>(g, images, targets, so, total);
+  else if (k == 3) pool_fwd_kernel<VEC, MAX, 3><<<grid, 256, 0, s>>>(g, images, targets, so, total);
+  else if (k == 4) pool_fwd_kernel<VEC, MAX, 4><<<grid, 256, 0, s>>>(g, images, targets, so, total);
+  else pool_fwd_kernel<VEC, MAX, 0><<<grid, 256, 0, s>>>(g, images, targets, so, total);
+}
+
 void pool_forward(const PoolGeom& g, bool is_max, const float* images, float* targets, float so) {
   const bool v4 = (g.N % 4 == 0) && aligned16(images) && aligned16(targets);
   const long long outs = (long long)g.modX * g.modY * g.C * g.modT;
-  cudaStream_t s = state().stream;
   if (v4) {
-    const long long total = outs * (g.N / 4);
-    if (is_max) pool_fwd_kernel<4, true><<<grid_for(total), 256, 0, s>>>(g, images, targets, so, total);
-    else pool_fwd_kernel<4, false><<<grid_for(total), 256, 0, s>>>(g, images, targets, so, total);
+    if (is_max) launch_fwd<4, true>(g, images, targets, so, outs * (g.N / 4));
+    else launch_fwd<4, false>(g, images, targets, so, outs * (g.N / 4));
   } else {
-    const long long total = outs * g.N;
-    if (is_max) pool_fwd_kernel<1, true><<<grid_for(total), 256, 0, s>>>(g, images, targets, so, total);
-    else pool_fwd_kernel<1, false><<<grid_for(total), 256, 0, s>>>(g, images, targets, so, total);
+    if (is_max) launch_fwd<1, true>(g, images, targets, so, outs * g.N);
+    else launch_fwd<1, false>(g, images, targets, so, outs * g.N);
   }
   count_launch();
   CNB_LAUNCH_CHECK("pool_forward");
+}
+
+template <int VEC, bool MAX>
+static void launch_undo(const PoolGeom& g, const float* images, const float* grads, const float* acts, float* targets,
+                        float st, float so, long long total) {
+  cudaStream_t s = state().stream;
+  const int grid = grid_for(total);
+  // windows covering one element per axis: ceil(k / stride)
+  const int q = (g.kt == 1 && g.T == 1 && g.modT == 1) ? std::max(ceil_div(g.kx, g.sx), ceil_div(g.ky, g.sy)) : 99;
+  if (q <= 1) pool_undo_kernel<VEC, MAX, 1><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total);
+  else if (q == 2) pool_undo_kernel<VEC, MAX, 2><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total);
+  else pool_undo_kernel<VEC, MAX, 0><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total);
 }
 
 static void undo(const PoolGeom& g, bool is_max, const float* images, const float* grads, const float* acts,
@@ -158,15 +226,12 @@ static void undo(const PoolGeom& g, bool is_max, const float* images, const floa
   const bool v4 = (g.N % 4 == 0) && aligned16(grads) && aligned16(targets) &&
                   (!is_max || (aligned16(images) && aligned16(acts)));
   const long long ins = (long long)g.W * g.H * g.C * g.T;
-  cudaStream_t s = state().stream;
   if (v4) {
-    const long long total = ins * (g.N / 4);
-    if (is_max) pool_undo_kernel<4, true><<<grid_for(total), 256, 0, s>>>(g, images, grads, acts, targets, st, so, total);
-    else pool_undo_kernel<4, false><<<grid_for(total), 256, 0, s>>>(g, images, grads, acts, targets, st, so, total);
+    if (is_max) launch_undo<4, true>(g, images, grads, acts, targets, st, so, ins * (g.N / 4));
+    else launch_undo<4, false>(g, images, grads, acts, targets, st, so, ins * (g.N / 4));
   } else {
-    const long long total = ins * g.N;
-    if (is_max) pool_undo_kernel<1, true><<<grid_for(total), 256, 0, s>>>(g, images, grads, acts, targets, st, so, total);
-    else pool_undo_kernel<1, false><<<grid_for(total), 256, 0, s>>>(g, images, grads, acts, targets, st, so, total);
+    if (is_max) launch_undo<1, true>(g, images, grads, acts, targets, st, so, ins * g.N);
+    else launch_undo<1, false>(g, images, grads, acts, targets, st, so, ins * g.N);
   }
   count_launch();
   CNB_LAUNCH_CHECK("pool_undo");

@@ -25,19 +25,22 @@ namespace cnb {
 
 constexpr int RN_THREADS = 128;
 
-// ring element (slot, thread): ring[slot * ring_stride + lane]
+// ring element (slot, thread): ring[slot * ring_stride + lane].
+// blockIdx.y selects a channel SEGMENT [f0, f1) (host: only when there are too few locations to fill the GPU); a
+// segment re-reads the k-1 (forward) / 2(k-1) (backward) halo channels of its neighbours instead of waiting for them.
 template <bool BLOCKED>
 __global__ void __launch_bounds__(RN_THREADS) rnorm_fwd_kernel(const float* __restrict__ x, float* __restrict__ y,
                                                                 long long L, int F, int k, float alpha, float beta,
-                                                                float* gring, long long gstride) {
+                                                                float* gring, long long gstride, int seg) {
   extern __shared__ float sring[];
   const long long loc = blockIdx.x * (long long)RN_THREADS + threadIdx.x;
   if (loc >= L) return;
-  float* ring = gring ? gring + loc : sring + threadIdx.x;
+  float* ring = gring ? gring + loc + (long long)blockIdx.y * k * gstride : sring + threadIdx.x;
   const long long rs = gring ? gstride : RN_THREADS;
   x += loc; y += loc;
-  if (BLOCKED) {
-    for (int s = 0; s < F; s += k) {
+  const int f0 = blockIdx.y * seg, f1 = min(F, f0 + seg);
+  if (BLOCKED) {                                        // host guarantees seg % k == 0
+    for (int s = f0; s < f1; s += k) {
       const int e = min(F, s + k);
       float sum = 0.f;
       for (int i = s; i < e; i++) { const float v = __ldg(x + (long long)i * L); ring[(i - s) * rs] = v; sum += v * v; }
@@ -49,23 +52,24 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_fwd_kernel(const float* __re
   const int a = k / 2, b = k - a - 1;
   float sum = 0.f;
   // q = entering channel; output channel j = q - b; window [j-a, j+b] = [q-k+1, q].
-  // Loads are hoisted four steps ahead of the (serial) ring updates to keep HBM requests in flight.
-  for (int q0 = 0; q0 < F + b; q0 += 4) {
-    float xv[4];
+  // Loads are hoisted eight steps ahead of the (serial) ring updates to keep HBM requests in flight.
+  const int q0 = max(0, f0 - a), q1 = f1 + b;      // channels >= F enter as zeros
+  for (int qb = q0; qb < q1; qb += 8) {
+    float xv[8];
 #pragma unroll
-    for (int u = 0; u < 4; u++) xv[u] = (q0 + u < F) ? __ldg(x + (long long)(q0 + u) * L) : 0.f;
+    for (int u = 0; u < 8; u++) xv[u] = (qb + u < F) ? __ldg(x + (long long)(qb + u) * L) : 0.f;
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const int q = q0 + u;
-      if (q >= F + b) break;
+    for (int u = 0; u < 8; u++) {
+      const int q = qb + u;
+      if (q >= q1) break;
       const int slot = q % k;
       const float v = xv[u];
       float old = 0.f;
-      if (q >= k) old = ring[slot * rs];
+      if (q - q0 >= k) old = ring[slot * rs];
       if (q < F) ring[slot * rs] = v;
       sum += v * v - old * old;
       const int j = q - b;
-      if (j >= 0) {
+      if (j >= f0 && j < f1) {
         const float xj = (j == q) ? v : ring[(j % k) * rs];
         y[(long long)j * L] = xj * __powf(1.f + alpha * sum, -beta);
       }
@@ -76,19 +80,21 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_fwd_kernel(const float* __re
 template <bool BLOCKED>
 __global__ void __launch_bounds__(RN_THREADS) rnorm_undo_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                  float* __restrict__ dx, long long L, int F, int k,
-                                                                 float alpha, float beta, float* gring, long long gstride) {
+                                                                 float alpha, float beta, float* gring, long long gstride,
+                                                                 int seg) {
   // three rings of k entries per thread: x, t = dy*x*denom, p = dy*denom^(beta/(beta+1))
   extern __shared__ float sring[];
   const long long loc = blockIdx.x * (long long)RN_THREADS + threadIdx.x;
   if (loc >= L) return;
   const long long rs = gring ? gstride : RN_THREADS;
-  float* rx = gring ? gring + loc : sring + threadIdx.x;
+  float* rx = gring ? gring + loc + (long long)blockIdx.y * 3 * k * gstride : sring + threadIdx.x;
   float* rt = rx + (long long)k * rs;
   float* rp = rt + (long long)k * rs;
   x += loc; dy += loc; dx += loc;
   const float c2 = 2.f * alpha * beta;
+  const int f0 = blockIdx.y * seg, f1 = min(F, f0 + seg);
   if (BLOCKED) {
-    for (int s = 0; s < F; s += k) {
+    for (int s = f0; s < f1; s += k) {
       const int e = min(F, s + k);
       float sum = 0.f;
       for (int i = s; i < e; i++) { const float v = __ldg(x + (long long)i * L); rx[(i - s) * rs] = v; sum += v * v; }
@@ -104,33 +110,35 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_undo_kernel(const float* __r
   float sumsq = 0.f, sumt = 0.f;
   // stage 1: entering channel q; channel i = q - b gets its forward sum, t_i and p_i
   // stage 2: output channel j = i - a gets sum of t over [j-b, j+a] = [i-k+1, i]
-  const int Q = F + b + a;
-  for (int q0 = 0; q0 < Q; q0 += 4) {
+  const int q0 = max(0, f0 - (k - 1));                   // first x needed: (f0 - b) - a
+  const int i0 = max(0, f0 - b);                         // first t needed
+  const int Qend = f1 + a + b;                           // last output f1-1 needs t up to f1-1+a, i.e. q up to f1-1+a+b
+  for (int qb = q0; qb < Qend; qb += 4) {
     float xv[4], gv[4];
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const int q = q0 + u, i = q - b;
+      const int q = qb + u, i = q - b;
       xv[u] = (q < F) ? __ldg(x + (long long)q * L) : 0.f;
-      gv[u] = (i >= 0 && i < F) ? __ldg(dy + (long long)i * L) : 0.f;
+      gv[u] = (i >= i0 && i < F) ? __ldg(dy + (long long)i * L) : 0.f;
     }
 #pragma unroll
     for (int u = 0; u < 4; u++) {
-      const int q = q0 + u;
-      if (q >= Q) break;
+      const int q = qb + u;
+      if (q >= Qend) break;
       {
         const int slot = q % k;
         const float v = xv[u];
         float old = 0.f;
-        if (q >= k) old = rx[slot * rs];
+        if (q - q0 >= k) old = rx[slot * rs];
         rx[slot * rs] = v;                              // zeros once q >= F
         sumsq += v * v - old * old;
       }
       const int i = q - b;
-      if (i < 0) continue;
+      if (i < i0) continue;
       {
         const int slot = i % k;
         float told = 0.f, t = 0.f;
-        if (i >= k) told = rt[slot * rs];
+        if (i - i0 >= k) told = rt[slot * rs];
         if (i < F) {
           const float base = 1.f + alpha * sumsq;
           const float g = gv[u];
@@ -142,7 +150,7 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_undo_kernel(const float* __r
         sumt += t - told;
       }
       const int j = i - a;
-      if (j >= 0 && j < F) {
+      if (j >= f0 && j < f1) {
         const int slot = j % k;
         dx[(long long)j * L] = rp[slot * rs] - c2 * rx[slot * rs] * sumt;
       }
@@ -152,16 +160,30 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_undo_kernel(const float* __r
 
 static constexpr size_t kMaxRingSmem = 160 * 1024;
 
+// channel segments per location: 1 unless the location count cannot fill the GPU
+static int pick_segments(long long L, int F, int k, bool blocked) {
+  const long long blocks = ceil_div<long long>(L, RN_THREADS);
+  const long long want = ceil_div<long long>(2LL * num_sms(), blocks);
+  int segs = (int)std::min<long long>(want, std::max(1, F / std::max(k, 1)));      // segment >= k: halo <= 2x / 3x reads
+  if (segs < 1) segs = 1;
+  (void)blocked;
+  return segs;
+}
+
 void rnorm_forward(const float* images, float* targets, long long L, int F, int k, float alpha, float beta,
                    bool blocked) {
   CNB_REQUIRE(k >= 1 && F >= 1, "ResponseNormCrossMap");
   const int blocks = (int)ceil_div<long long>(L, RN_THREADS);
+  int segs = pick_segments(L, F, k, blocked);
+  int seg = ceil_div(F, segs);
+  if (blocked) seg = ceil_div(seg, k) * k;
+  segs = ceil_div(F, seg);
   size_t smem = sizeof(float) * (size_t)k * RN_THREADS;
   float* gring = nullptr;
-  if (smem > kMaxRingSmem) { gring = (float*)workspace(sizeof(float) * (size_t)k * L); smem = 0; }
+  if (smem > kMaxRingSmem) { gring = (float*)workspace(sizeof(float) * (size_t)k * L * segs); smem = 0; }
   auto kern = blocked ? rnorm_fwd_kernel<true> : rnorm_fwd_kernel<false>;
   if (smem > 48 * 1024) CNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<blocks, RN_THREADS, smem, state().stream>>>(images, targets, L, F, k, alpha, beta, gring, L);
+  kern<<<dim3(blocks, segs), RN_THREADS, smem, state().stream>>>(images, targets, L, F, k, alpha, beta, gring, L, seg);
   count_launch();
   CNB_LAUNCH_CHECK("rnorm_forward");
 }
@@ -170,12 +192,16 @@ void rnorm_undo(const float* outGrads, const float* inputs, float* targets, long
                 float alpha, float beta, bool blocked) {
   CNB_REQUIRE(k >= 1 && F >= 1, "ResponseNormCrossMapUndo");
   const int blocks = (int)ceil_div<long long>(L, RN_THREADS);
+  int segs = pick_segments(L, F, k, blocked);
+  int seg = ceil_div(F, segs);
+  if (blocked) seg = ceil_div(seg, k) * k;
+  segs = ceil_div(F, seg);
   size_t smem = sizeof(float) * 3 * (size_t)k * RN_THREADS;
   float* gring = nullptr;
-  if (smem > kMaxRingSmem) { gring = (float*)workspace(sizeof(float) * 3 * (size_t)k * L); smem = 0; }
+  if (smem > kMaxRingSmem) { gring = (float*)workspace(sizeof(float) * 3 * (size_t)k * L * segs); smem = 0; }
   auto kern = blocked ? rnorm_undo_kernel<true> : rnorm_undo_kernel<false>;
   if (smem > 48 * 1024) CNB_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  kern<<<blocks, RN_THREADS, smem, state().stream>>>(outGrads, inputs, targets, L, F, k, alpha, beta, gring, L);
+  kern<<<dim3(blocks, segs), RN_THREADS, smem, state().stream>>>(outGrads, inputs, targets, L, F, k, alpha, beta, gring, L, seg);
   count_launch();
   CNB_LAUNCH_CHECK("rnorm_undo");
 }
