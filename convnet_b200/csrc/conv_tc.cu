@@ -436,25 +436,36 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       ptx::mbar_wait(&ctl->tmem_full[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * p.BN);
-      for (int j0 = 0; j0 < p.BN; j0 += 32) {
+      // three store flavours, chosen once per tile so that the unrolled 32-column bodies stay small (the fully
+      // general body thrashed the instruction cache: stall_no_inst dominated the epilogue-bound shapes)
+      const float so_eff = direct_scale ? p.so : 1.f;
+      const bool rmw = direct_scale && p.st != 0.f;
+      const bool scatter = (OP == kWgrad) && p.x_mode;
+      for (int j0 = 0; j0 < ncols_valid; j0 += 32) {
         float v[32];
         ptx::tmem_ld_32x32(t_addr + j0, v);
         ptx::tmem_ld_wait();
-        if (row_ptr != nullptr) {
+        if (row_ptr == nullptr) continue;
+        const int nv = ncols_valid - j0;                 // > 0
+        if (scatter) {
 #pragma unroll
           for (int j = 0; j < 32; j++) {
-            if (j0 + j < ncols_valid) {
-              float* dst = row_ptr + col_stride * (j0 + j);
-              if (OP == kWgrad && p.x_mode) {
-                const int jg = j0 + j, tx = jg & 7, rr = jg >> 3, ty = rr % p.ky, c = tile.c_tile * p.x_ct + rr / p.ky;
-                if (tx >= p.kx || c >= p.Cin) continue;
-                dst = row_ptr + (long long)p.Cout * (tx + p.kx * (ty + p.ky * c));
-              }
-              float r = v[j];
-              if (direct_scale) r = (p.st == 0.f) ? p.so * r : p.st * (*dst) + p.so * r;
-              *dst = r;
+            const int jg = j0 + j, tx = jg & 7, rr = jg >> 3, ty = rr % p.ky, c = tile.c_tile * p.x_ct + rr / p.ky;
+            if (j < nv && tx < p.kx && c < p.Cin) {
+              float* dst = row_ptr + (long long)p.Cout * (tx + p.kx * (ty + p.ky * c));
+              *dst = rmw ? p.st * (*dst) + so_eff * v[j] : so_eff * v[j];
             }
           }
+        } else if (rmw) {
+          float* dst = row_ptr + col_stride * j0;
+#pragma unroll
+          for (int j = 0; j < 32; j++, dst += col_stride)
+            if (j < nv) *dst = p.st * (*dst) + so_eff * v[j];
+        } else {
+          float* dst = row_ptr + col_stride * j0;
+#pragma unroll
+          for (int j = 0; j < 32; j++, dst += col_stride)
+            if (j < nv) *dst = so_eff * v[j];
         }
       }
       ptx::tc_fence_before();

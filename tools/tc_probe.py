@@ -26,6 +26,7 @@ SHAPES = {
     "conv5": (256, 14, 14, 384, 512, 3, 3, 1, 1, 0, 0),
     "conv2": (256, 55, 55, 96, 256, 5, 5, 2, 2, 1, 1),
     "fc7": (256, 1, 1, 4096, 4096, 1, 1, 1, 1, 0, 0),
+    "fc6": (128, 1, 1, 18432, 4096, 1, 1, 1, 1, 0, 0),
     "conv1_small": (32, 21, 21, 3, 16, 7, 7, 2, 2, 1, 1),
     "conv1": (128, 224, 224, 3, 96, 7, 7, 2, 2, 1, 1),
     "mnist1": (100, 28, 28, 1, 48, 4, 4, 1, 1, 0, 0),
