@@ -5,6 +5,7 @@
 
 #include "../../include/convnet_b200_conv.h"
 #include "../../include/convnet_b200_conv_gemm.h"
+#include "../../include/convnet_b200_ext.h"
 #include "conv_kernels.h"
 
 using namespace cnb;
@@ -15,15 +16,24 @@ ConvDesc as_2d(ConvDesc d) { d.kernel_size_t = 1; d.stride_t = 1; d.padding_t = 
 
 // ---- dispatch: tensor-core path when the mode and the shape allow, else fp32 CUDA cores
 void conv_up(const ConvGeom& g, const float* images, const float* filters, float* targets, float st, float so) {
-  if (state().precision != kPrecFP32 && tc_conv_up(g, images, filters, targets, st, so)) return;
-  simt_conv_up(g, images, filters, targets, st, so);
+  Fuse fuse = take_fuse();
+  if (!g.conv && fuse.any()) { fprintf(stderr, "convnet_b200: epilogue fusion is not available for untied filters\n"); abort(); }
+  if (state().precision != kPrecFP32 && tc_conv_up(g, images, filters, targets, st, so, fuse)) return;
+  simt_conv_up(g, images, filters, targets, st, so, fuse);
   state().last_conv_path = kPathSimt;
 }
 
 void conv_down(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float st, float so) {
-  if (state().precision != kPrecFP32 && tc_conv_down(g, derivs, filters, targets, st, so)) return;
-  simt_conv_down(g, derivs, filters, targets, st, so);
-  state().last_conv_path = kPathSimt;
+  Fuse fuse = take_fuse();
+  // the mask can ride in the epilogue only when one launch produces the final value of every target element
+  const bool whole = g.conv && g.frames == 1 && g.cin0 == 0 && g.Cin == g.CinT;
+  const float* late_mask = nullptr;
+  if (fuse.relu_mask && !whole) { late_mask = fuse.relu_mask; fuse.relu_mask = nullptr; }
+  if (!(state().precision != kPrecFP32 && tc_conv_down(g, derivs, filters, targets, st, so, fuse))) {
+    simt_conv_down(g, derivs, filters, targets, st, so, fuse);
+    state().last_conv_path = kPathSimt;
+  }
+  if (late_mask) cnb_relu_deriv(targets, late_mask, g.img_total);
 }
 
 // reduction split for the CUDA-core wgrad: enough (tile x chunk) blocks to fill the GPU
@@ -75,12 +85,15 @@ void do_max_undo(const char* what, cudamat* images, cudamat* maxGrads, cudamat* 
   PoolGeom g = pool_geom(*is, *gs, images, maxGrads, d, what);
   CNB_REQUIRE(targets->size[0] == g.N && targets->size[1] == images->size[1], what);
   CNB_REQUIRE(maxActs->size[0] == g.N && maxActs->size[1] == maxGrads->size[1], what);
-  max_pool_undo(g, images->data_device, maxGrads->data_device, maxActs->data_device, targets->data_device, st, 1.f);
+  const Fuse fuse = take_fuse();
+  max_pool_undo(g, images->data_device, maxGrads->data_device, maxActs->data_device, targets->data_device, st, 1.f,
+                fuse.relu_mask);
 }
 void do_avg_undo(const char* what, cudamat* avgGrads, cudamat* targets, Shape4D* gs, Shape4D* ts, ConvDesc d, float st,
                  float so) {
   PoolGeom g = pool_geom(*ts, *gs, targets, avgGrads, d, what);
-  avg_pool_undo(g, avgGrads->data_device, targets->data_device, st, so);
+  const Fuse fuse = take_fuse();
+  avg_pool_undo(g, avgGrads->data_device, targets->data_device, st, so, fuse.relu_mask);
 }
 
 ConvDesc sample_desc(Shape4D* is, Shape4D* ts, int factor) {      // gemm.cu:1503-1541

@@ -49,6 +49,14 @@ namespace cnb {
 enum Precision { kPrecFP32 = 0, kPrecTF32 = 1, kPrecBF16 = 2 };
 enum ConvPath { kPathNone = -1, kPathSimt = 0, kPathTcTf32 = 1, kPathTcBf16 = 2 };
 
+// one-shot epilogue fusion requested for the next conv / pool-undo call (convnet_b200_fuse_next)
+struct Fuse {
+  const float* bias = nullptr;       // fprop: + bias[output channel]
+  int relu = 0;                      // fprop: max(., 0) after the bias
+  const float* relu_mask = nullptr;  // dgrad / pool undo: result zeroed where relu_mask <= 0 (same shape as the target)
+  bool any() const { return bias || relu || relu_mask; }
+};
+
 struct State {
   cudaStream_t stream = 0;          // legacy default stream, like every reference kernel
   int precision = kPrecTF32;
@@ -60,13 +68,16 @@ struct State {
   int ws_device = -1;
   int num_sms = 0;
   int sm_device = -1;
+  Fuse fuse;
 };
+inline Fuse take_fuse();
 State& state();
 
 void* workspace(size_t bytes);       // device scratch of at least `bytes`, valid until next call
 int num_sms();
 
 inline void count_launch(int n = 1) { state().launches += n; }
+inline Fuse take_fuse() { Fuse f = state().fuse; state().fuse = Fuse(); return f; }
 
 template <typename T>
 __host__ __device__ inline T ceil_div(T a, T b) { return (a + b - 1) / b; }

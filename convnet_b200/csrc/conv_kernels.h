@@ -7,9 +7,9 @@ namespace cnb {
 
 // conv_simt.cu — fp32 CUDA-core implicit GEMM (exact mode + shapes the tensor path skips)
 void simt_conv_up(const ConvGeom& g, const float* images, const float* filters, float* targets,
-                  float scaleTargets, float scaleOutput);
+                  float scaleTargets, float scaleOutput, const Fuse& fuse);
 void simt_conv_down(const ConvGeom& g, const float* derivs, const float* filters, float* targets,
-                    float scaleTargets, float scaleOutput);
+                    float scaleTargets, float scaleOutput, const Fuse& fuse);
 // rectH x rectW: module rectangle per reduction chunk; keep_partials: one output block per chunk
 void simt_conv_outp(const ConvGeom& g, const float* images, const float* derivs, float* targets,
                     int rectH, int rectW, bool keep_partials, float scaleTargets, float scaleOutput);
@@ -18,18 +18,18 @@ void reduce_partials(const float* part, float* out, long long elems, int groups,
 
 // conv_tc.cu — tcgen05 / TMA implicit GEMM (sm_100a tensor cores)
 bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, float* targets,
-                float scaleTargets, float scaleOutput);
+                float scaleTargets, float scaleOutput, const Fuse& fuse);
 bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, float* targets,
-                  float scaleTargets, float scaleOutput);
+                  float scaleTargets, float scaleOutput, const Fuse& fuse);
 bool tc_conv_outp(const ConvGeom& g, const float* images, const float* derivs, float* targets,
                   float scaleTargets, float scaleOutput);
 
 // pool.cu
 void pool_forward(const PoolGeom& g, bool is_max, const float* images, float* targets, float scaleOutput);
 void max_pool_undo(const PoolGeom& g, const float* images, const float* maxGrads, const float* maxActs,
-                   float* targets, float scaleTargets, float scaleOutput);
+                   float* targets, float scaleTargets, float scaleOutput, const float* relu_mask);
 void avg_pool_undo(const PoolGeom& g, const float* avgGrads, float* targets, float scaleTargets,
-                   float scaleOutput);
+                   float scaleOutput, const float* relu_mask);
 
 // rnorm.cu
 void rnorm_forward(const float* images, float* targets, long long num_locs, int numFilters, int sizeF,

@@ -27,6 +27,7 @@ struct FpropProblem {
   long long flt_z, img_z, out_z;  // per-blockIdx.z strides (untied module / 3-D frame)
   int z_is_module;              // untied: z = module and M = N
   float st, so;
+  const float* bias; int relu;  // fused epilogue (convnet_b200_fuse_next)
   __device__ __forceinline__ long long rows() const { return M; }
   __device__ __forceinline__ int cols() const { return Cout; }
   __device__ __forceinline__ int depth() const { return K; }
@@ -47,7 +48,10 @@ struct FpropProblem {
   }
   __device__ __forceinline__ void store(long long m, int o, float acc, int z) const {
     float* t = out + (z_is_module ? (long long)z * N : z * out_z) + m + (long long)N * modules * o;
-    *t = (st == 0.f) ? so * acc : st * (*t) + so * acc;
+    float r = (st == 0.f) ? so * acc : st * (*t) + so * acc;
+    if (bias) r += __ldg(bias + o);
+    if (relu) r = fmaxf(r, 0.f);
+    *t = r;
   }
 };
 
@@ -59,6 +63,7 @@ struct DgradProblem {
   long long der_z, out_z;       // 3-D frame strides (sequential launches use z = 0)
   int untied;
   float st, so;
+  const float* mask;            // fused ReLU derivative: same layout as out
   __device__ __forceinline__ long long rows() const { return M; }
   __device__ __forceinline__ int cols() const { return Cin; }
   __device__ __forceinline__ int depth() const { return K; }
@@ -86,7 +91,9 @@ struct DgradProblem {
   }
   __device__ __forceinline__ void store(long long m, int c, float acc, int z) const {
     float* t = out + z * out_z + m + M * c;
-    *t = (st == 0.f) ? so * acc : st * (*t) + so * acc;
+    float r = (st == 0.f) ? so * acc : st * (*t) + so * acc;
+    if (mask && !(__ldg(mask + z * out_z + m + M * c) > 0.f)) r = 0.f;
+    *t = r;
   }
 };
 
@@ -281,8 +288,9 @@ void reduce_partials(const float* part, float* out, long long elems, int groups,
 
 // ---- host entry points -------------------------------------------------------------
 void simt_conv_up(const ConvGeom& g, const float* images, const float* filters, float* targets,
-                  float scaleTargets, float scaleOutput) {
+                  float scaleTargets, float scaleOutput, const Fuse& fuse) {
   FpropProblem p;
+  p.bias = fuse.bias ? fuse.bias + g.cout0 : nullptr; p.relu = fuse.relu;
   p.img = images + (long long)g.cin0 * g.H * g.W * g.N;
   p.flt = filters;
   p.out = targets + (long long)g.cout0 * g.modules * g.N;
@@ -316,9 +324,10 @@ void simt_local_down(const ConvGeom& g, const float* derivs, const float* filter
 }
 
 void simt_conv_down(const ConvGeom& g, const float* derivs, const float* filters, float* targets,
-                    float scaleTargets, float scaleOutput) {
+                    float scaleTargets, float scaleOutput, const Fuse& fuse) {
   if (!g.conv) { simt_local_down(g, derivs, filters, targets, scaleTargets, scaleOutput); return; }
   DgradProblem p;
+  p.mask = nullptr;
   p.der = derivs + (long long)g.cout0 * g.modules * g.N;
   p.flt = filters;
   p.out = targets + (long long)g.cin0 * g.H * g.W * g.N;
@@ -330,6 +339,7 @@ void simt_conv_down(const ConvGeom& g, const float* derivs, const float* filters
   // The reference scales the WHOLE target (all channels, all frames) first (gemm.cu:760, conv3d:98).
   if (g.frames == 1 && g.cin0 == 0 && g.Cin == g.CinT) {
     p.st = scaleTargets;
+    p.mask = fuse.relu_mask;
     launch(p, p.M, g.Cin, 1);
     return;
   }

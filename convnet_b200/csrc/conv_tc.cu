@@ -58,6 +58,8 @@ struct TcParams {
   int splits, units_per_split;      // wgrad: (frame, module-row) units per reduction split
   float* out;
   float st, so;
+  const float* bias; int relu;      // fused fprop epilogue: + bias[o], then max(., 0)
+  const float* mask;                // fused dgrad epilogue: zero where mask <= 0 (same layout as out)
   long long out_frame_step;         // fprop: floats between output frames
   uint32_t idesc;
 };
@@ -441,6 +443,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const float so_eff = direct_scale ? p.so : 1.f;
       const bool rmw = direct_scale && p.st != 0.f;
       const bool scatter = (OP == kWgrad) && p.x_mode;
+      const bool fused = (OP == kFprop && (p.bias != nullptr || p.relu)) || (OP == kDgrad && p.mask != nullptr);
       for (int j0 = 0; j0 < ncols_valid; j0 += 32) {
         float v[32];
         ptx::tmem_ld_32x32(t_addr + j0, v);
@@ -456,6 +459,20 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               *dst = rmw ? p.st * (*dst) + so_eff * v[j] : so_eff * v[j];
             }
           }
+        } else if (fused) {
+          float* dst = row_ptr + col_stride * j0;
+          const float* bias = (OP == kFprop && p.bias) ? p.bias + tile.n_tile * p.BN + j0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j++, dst += col_stride)
+            if (j < nv) {
+              float r = so_eff * v[j];
+              if (rmw) r += p.st * (*dst);
+              if (OP == kFprop) {
+                if (bias) r += __ldg(bias + j);
+                if (p.relu) r = fmaxf(r, 0.f);
+              } else if (!(__ldg(p.mask + (dst - p.out)) > 0.f)) r = 0.f;
+              *dst = r;
+            }
         } else if (rmw) {
           float* dst = row_ptr + col_stride * j0;
 #pragma unroll
@@ -573,6 +590,7 @@ void fill_common(TcParams& p, const ConvGeom& g) {
   p.splits = 1; p.units_per_split = 0;
   p.x_mode = 0; p.x_yblocks = 0; p.x_ct = 0; p.b_tx_bytes = 0;
   p.a_merged = 0; p.b_merged = 0;
+  p.bias = nullptr; p.relu = 0; p.mask = nullptr;
   p.out_frame_step = g.out_frame_step;
 }
 
@@ -610,7 +628,8 @@ bool merged_image_map(CUtensorMap* m, const float* base, const ConvGeom& g, int 
 }  // namespace
 
 // ---- fprop ---------------------------------------------------------------------------------------
-bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, float* targets, float st, float so) {
+bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, float* targets, float st, float so,
+                const Fuse& fuse) {
   if (!tc_enabled() || !g.conv) return false;
   if (g.N % 4 != 0 || g.Cout % 4 != 0) return false;                        // TMA stride alignment
   const bool x_mode = g.Cin < 8;                                            // tiny channel counts: taps take the K block
@@ -629,6 +648,7 @@ bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, fl
   p.num_tiles = p.m_tiles * p.n_tiles;
   p.out = targets + (long long)g.cout0 * g.modules * g.N;
   p.st = st; p.so = so;
+  p.bias = fuse.bias ? fuse.bias + g.cout0 : nullptr; p.relu = fuse.relu;
   p.idesc = ptx::make_idesc(2, true, true, BM, p.BN);
   CUtensorMap ma, mb;
   const float* img = images + (long long)g.cin0 * g.H * g.W * g.N;
@@ -680,7 +700,8 @@ bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, fl
 }
 
 // ---- dgrad ---------------------------------------------------------------------------------------
-bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float st, float so) {
+bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float st, float so,
+                  const Fuse& fuse) {
   if (!tc_enabled() || !g.conv) return false;
   if (g.N % 4 != 0 || g.Cout % 4 != 0 || g.Cout < 8 || g.Cin < 8) return false;
   TcParams p; fill_common(p, g);
@@ -711,7 +732,7 @@ bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, 
   float* out = targets + (long long)g.cin0 * g.H * g.W * g.N;
   const bool whole = (g.frames == 1 && g.cin0 == 0 && g.Cin == g.CinT);
   if (whole) {
-    p.st = st; p.out = out;
+    p.st = st; p.out = out; p.mask = fuse.relu_mask ? fuse.relu_mask + (long long)g.cin0 * g.H * g.W * g.N : nullptr;
     launch<kDgrad>(ma, mb, p);
   } else {
     // the reference scales the WHOLE target first (gemm.cu:760, conv3d_gemm.cu:98); frame windows overlap,

@@ -72,6 +72,9 @@ void convnet_b200_set_conv_precision(int mode) {
   state().precision = mode;
 }
 int convnet_b200_get_conv_precision(void) { return state().precision; }
+void convnet_b200_fuse_next(const float* bias, int relu, const float* relu_mask) {
+  state().fuse.bias = bias; state().fuse.relu = relu; state().fuse.relu_mask = relu_mask;
+}
 int convnet_b200_last_conv_path(void) { return state().last_conv_path; }
 unsigned long long convnet_b200_launch_count(void) { return state().launches; }
 void convnet_b200_reset_launch_count(void) { state().launches = 0; }

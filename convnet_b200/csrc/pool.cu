@@ -108,7 +108,8 @@ template <int VEC, bool MAX, int Q>
 __global__ void __launch_bounds__(256) pool_undo_kernel(PoolGeom g, const float* __restrict__ images,
                                                          const float* __restrict__ grads,
                                                          const float* __restrict__ acts, float* targets,
-                                                         float st, float so, long long total) {
+                                                         float st, float so, long long total,
+                                                         const float* __restrict__ relu_mask) {
   const int NV = g.N / VEC;
   for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
        idx += (long long)gridDim.x * blockDim.x) {
@@ -173,6 +174,12 @@ __global__ void __launch_bounds__(256) pool_undo_kernel(PoolGeom g, const float*
     }
 #pragma unroll
     for (int v = 0; v < VEC; v++) acc[v] += st * old[v];
+    if (relu_mask) {                           // fused ApplyDerivativeOfActivation of the layer receiving this derivative
+      float mk[VEC];
+      vload<VEC>(relu_mask + idx * VEC, mk);
+#pragma unroll
+      for (int v = 0; v < VEC; v++) acc[v] = mk[v] > 0.f ? acc[v] : 0.f;
+    }
     vstore<VEC>(targets + idx * VEC, acc);
   }
 }
@@ -211,39 +218,39 @@ void pool_forward(const PoolGeom& g, bool is_max, const float* images, float* ta
 
 template <int VEC, bool MAX>
 static void launch_undo(const PoolGeom& g, const float* images, const float* grads, const float* acts, float* targets,
-                        float st, float so, long long total) {
+                        float st, float so, long long total, const float* mask) {
   cudaStream_t s = state().stream;
   const int grid = grid_for(total);
   // windows covering one element per axis: ceil(k / stride)
   const int q = (g.kt == 1 && g.T == 1 && g.modT == 1) ? std::max(ceil_div(g.kx, g.sx), ceil_div(g.ky, g.sy)) : 99;
-  if (q <= 1) pool_undo_kernel<VEC, MAX, 1><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total);
-  else if (q == 2) pool_undo_kernel<VEC, MAX, 2><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total);
-  else pool_undo_kernel<VEC, MAX, 0><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total);
+  if (q <= 1) pool_undo_kernel<VEC, MAX, 1><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total, mask);
+  else if (q == 2) pool_undo_kernel<VEC, MAX, 2><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total, mask);
+  else pool_undo_kernel<VEC, MAX, 0><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total, mask);
 }
 
 static void undo(const PoolGeom& g, bool is_max, const float* images, const float* grads, const float* acts,
-                 float* targets, float st, float so) {
-  const bool v4 = (g.N % 4 == 0) && aligned16(grads) && aligned16(targets) &&
+                 float* targets, float st, float so, const float* mask) {
+  const bool v4 = (g.N % 4 == 0) && aligned16(grads) && aligned16(targets) && (!mask || aligned16(mask)) &&
                   (!is_max || (aligned16(images) && aligned16(acts)));
   const long long ins = (long long)g.W * g.H * g.C * g.T;
   if (v4) {
-    if (is_max) launch_undo<4, true>(g, images, grads, acts, targets, st, so, ins * (g.N / 4));
-    else launch_undo<4, false>(g, images, grads, acts, targets, st, so, ins * (g.N / 4));
+    if (is_max) launch_undo<4, true>(g, images, grads, acts, targets, st, so, ins * (g.N / 4), mask);
+    else launch_undo<4, false>(g, images, grads, acts, targets, st, so, ins * (g.N / 4), mask);
   } else {
-    if (is_max) launch_undo<1, true>(g, images, grads, acts, targets, st, so, ins * g.N);
-    else launch_undo<1, false>(g, images, grads, acts, targets, st, so, ins * g.N);
+    if (is_max) launch_undo<1, true>(g, images, grads, acts, targets, st, so, ins * g.N, mask);
+    else launch_undo<1, false>(g, images, grads, acts, targets, st, so, ins * g.N, mask);
   }
   count_launch();
   CNB_LAUNCH_CHECK("pool_undo");
 }
 
 void max_pool_undo(const PoolGeom& g, const float* images, const float* maxGrads, const float* maxActs,
-                   float* targets, float st, float so) {
-  undo(g, true, images, maxGrads, maxActs, targets, st, so);
+                   float* targets, float st, float so, const float* relu_mask) {
+  undo(g, true, images, maxGrads, maxActs, targets, st, so, relu_mask);
 }
 
-void avg_pool_undo(const PoolGeom& g, const float* avgGrads, float* targets, float st, float so) {
-  undo(g, false, nullptr, avgGrads, nullptr, targets, st, so);
+void avg_pool_undo(const PoolGeom& g, const float* avgGrads, float* targets, float st, float so, const float* relu_mask) {
+  undo(g, false, nullptr, avgGrads, nullptr, targets, st, so, relu_mask);
 }
 
 }  // namespace cnb

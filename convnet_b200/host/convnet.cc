@@ -46,6 +46,7 @@ void Layer::AllocateMemory(int batch_size) {               // layer.cc:228-262 (
 }
 
 void Layer::ApplyActivation() {
+  if (activation_fused_) return;
   switch (config_.activation) {
     case LINEAR: break;
     case RECTIFIED_LINEAR: state_.ApplyReLU(); break;      // LowerBound(0), layer.cc:550
@@ -53,6 +54,7 @@ void Layer::ApplyActivation() {
   }
 }
 void Layer::ApplyDerivativeOfActivation() {
+  if (deriv_fused_) return;
   if (config_.activation == RECTIFIED_LINEAR) deriv_.ApplyDerivOfReLU(state_);
 }
 void Layer::ApplyDropout(bool train, unsigned long long step) {      // layer.cc:367-395, scale-up at train time
@@ -172,12 +174,32 @@ ConvNet::ConvNet(const ModelConfig& model, int batch_size) : model_(model), batc
     e->SetBatchSize(batch_size);
     edges_.push_back(e);
   }
+  // epilogue fusion of the Layer-side ReLU / ReLU' into the neighbouring edges
+  const char* nf = getenv("CONVNET_B200_NO_FUSE");
+  if (!(nf && nf[0] == '1')) {
+    for (size_t i = 0; i < edges_.size(); i++) {
+      Layer *src = layers_[i], *dst = layers_[i + 1];
+      if (dst->GetActivation() == RECTIFIED_LINEAR && model.edge[i].edge_type != RESPONSE_NORM) {
+        edges_[i]->SetFuseReLU(true);              // honoured only where CanFuseReLU() (checked after SetImageSize below)
+      }
+      if (!src->IsInput() && src->GetActivation() == RECTIFIED_LINEAR) edges_[i]->SetFuseMask(true);
+    }
+  }
   // SetImageSize propagation (convnet.cc:226-268)
   const LayerConfig& in = model.layer.front();
   layers_[0]->SetSize(in.image_size_y, in.image_size_x, in.image_size_t);
   for (size_t i = 0; i < edges_.size(); i++) {
     edges_[i]->SetImageSize(layers_[i]->GetSizeY(), layers_[i]->GetSizeX(), layers_[i]->GetSizeT());
     layers_[i + 1]->SetSize(edges_[i]->GetNumModulesY(), edges_[i]->GetNumModulesX(), edges_[i]->GetNumModulesT());
+  }
+  for (size_t i = 0; i < edges_.size(); i++) {       // settle the fusion flags now that shapes are known
+    Edge* e = edges_[i];
+    const bool relu = layers_[i + 1]->GetActivation() == RECTIFIED_LINEAR && e->CanFuseReLU() && e->WantsFuseReLU();
+    e->SetFuseReLU(relu);
+    layers_[i + 1]->SetActivationFused(relu);
+    const bool mask = e->CanFuseMask() && e->WantsFuseMask();
+    e->SetFuseMask(mask);
+    layers_[i]->SetDerivFused(mask);
   }
 }
 

@@ -55,6 +55,9 @@ class Layer {                                   // src/layer.{h,cc}, reduced to 
   int GetSizeX() const { return image_size_x_; }
   int GetSizeT() const { return image_size_t_; }
   const std::string& GetName() const { return config_.name; }
+  Activation GetActivation() const { return config_.activation; }
+  void SetActivationFused(bool v) { activation_fused_ = v; }      // the incoming edge applies the ReLU in its epilogue
+  void SetDerivFused(bool v) { deriv_fused_ = v; }                // the outgoing edge applies ReLU' in its epilogue
   ~Layer();
 
  private:
@@ -62,6 +65,7 @@ class Layer {                                   // src/layer.{h,cc}, reduced to 
   int image_size_y_, image_size_x_, image_size_t_;
   Matrix state_, deriv_, loss_per_image_, dropout_mask_;
   int* labels_ = nullptr;
+  bool activation_fused_ = false, deriv_fused_ = false;
 };
 
 // NCCL all-reduce of the flat gradient buffer, bucketed along edge boundaries and launched on a side

@@ -151,12 +151,14 @@ void ConvEdge::SetGradMemory(Matrix& p) {                    // :108-136
 void ConvEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) {   // :138-170
   const float scale_targets = overwrite ? 0 : 1;
   const int mods = num_modules_y_ * num_modules_x_ * num_modules_t_;
+  const bool fused = fuse_relu_ && CanFuseReLU();        // bias (+ReLU of the destination layer) in the conv epilogue
   if (image_size_t_ == 1) {
+    if (fused) convnet_b200_fuse_next(bias_.GetDevData(), 1, nullptr);
     Matrix::ConvUp(input, weights_, output, conv_desc_, scale_targets);
   } else {
     Matrix::Conv3DUp(input, weights_, output, conv_desc_, scale_targets);
   }
-  if (!has_no_bias_) {
+  if (!has_no_bias_ && !fused) {
     if (shared_bias_ && image_size_t_ == 1) {
       output.Reshape(-1, conv_desc_.num_output_channels);
       output.AddRowVec(bias_);
@@ -178,6 +180,7 @@ void ConvEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool tra
 void ConvEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input,
                            bool overwrite) {                 // :172-181
   const float scale_targets = overwrite ? 0 : 1;
+  if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());      // ReLU' of the source layer
   if (image_size_t_ == 1) Matrix::ConvDown(deriv_output, weights_, deriv_input, conv_desc_, scale_targets);
   else Matrix::Conv3DDown(deriv_output, weights_, deriv_input, conv_desc_, scale_targets);
 }
@@ -256,13 +259,16 @@ void FCEdge::View(Matrix& in, Matrix& out) {
 void FCEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) {      // fc_edge.cc:51-60
   Shape4D si = input.GetShape4D(), so = output.GetShape4D();
   View(input, output);
+  const bool fused = fuse_relu_ && !has_no_bias_;
+  if (fused) convnet_b200_fuse_next(bias_.GetDevData(), 1, nullptr);
   Matrix::ConvUp(input, weights_, output, desc_, overwrite ? 0 : 1);     // output = input * W^T
-  if (!has_no_bias_) output.AddRowVec(bias_);
+  if (!has_no_bias_ && !fused) output.AddRowVec(bias_);
   input.GetShape4D() = si; output.GetShape4D() = so;
 }
 void FCEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) {
   Shape4D si = deriv_input.GetShape4D(), so = deriv_output.GetShape4D();
   View(deriv_input, deriv_output);
+  if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
   Matrix::ConvDown(deriv_output, weights_, deriv_input, desc_, overwrite ? 0 : 1);
   deriv_input.GetShape4D() = si; deriv_output.GetShape4D() = so;
 }
@@ -300,8 +306,10 @@ void ConvOneToOneEdge::SetGradMemory(Matrix& p) {
 }
 void ConvOneToOneEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) {   // :56-73
   const int batch_size = input.GetRows();
+  const bool fused = fuse_relu_ && !has_no_bias_;
+  if (fused) convnet_b200_fuse_next(bias_.GetDevData(), 1, nullptr);
   Matrix::ConvUp(input, weights_, output, desc_, overwrite ? 0 : 1);
-  if (!has_no_bias_) {
+  if (!has_no_bias_ && !fused) {
     output.Reshape(-1, num_output_channels_);
     output.AddRowVec(bias_);
     output.Reshape(batch_size, -1);
@@ -309,6 +317,7 @@ void ConvOneToOneEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, 
 }
 void ConvOneToOneEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input,
                                    bool overwrite) {
+  if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
   Matrix::ConvDown(deriv_output, weights_, deriv_input, desc_, overwrite ? 0 : 1);
 }
 void ConvOneToOneEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {                        // :87-102
@@ -346,6 +355,7 @@ void MaxPoolEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool 
   Matrix::ConvMaxPool(input, output, conv_desc_);
 }
 void MaxPoolEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) {
+  if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
   Matrix::ConvMaxPoolUndo(input, deriv_output, output, deriv_input, conv_desc_, overwrite ? 0 : 1);
 }
 void AvgPoolEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) {   // avgpool_edge.cc:50-58
@@ -353,6 +363,7 @@ void AvgPoolEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool 
   Matrix::ConvAvgPool(input, output, conv_desc_);
 }
 void AvgPoolEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) {
+  if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
   Matrix::ConvAvgPoolUndo(deriv_output, deriv_input, conv_desc_, overwrite ? 0 : 1);
 }
 

@@ -81,6 +81,14 @@ class Edge {
   void SetSource(Layer* l) { source_ = l; }
   void SetDest(Layer* l) { dest_ = l; }
   void SetBatchSize(int n) { batch_size_ = n; }
+  // Epilogue fusion (convnet_b200_fuse_next): the ReLU of the destination layer rides in ComputeUp's conv epilogue
+  // (together with the shared bias), the ReLU derivative of the source layer in ComputeDown's. ConvNet decides.
+  virtual bool CanFuseReLU() const { return false; }
+  virtual bool CanFuseMask() const { return false; }
+  void SetFuseReLU(bool v) { fuse_relu_ = v; }
+  void SetFuseMask(bool v) { fuse_mask_ = v; }
+  bool WantsFuseReLU() const { return fuse_relu_; }
+  bool WantsFuseMask() const { return fuse_mask_; }
 
  protected:
   EdgeConfig config_;
@@ -90,6 +98,7 @@ class Edge {
   int image_size_y_, image_size_x_, image_size_t_;
   int num_modules_y_, num_modules_x_, num_modules_t_;
   int batch_size_;
+  bool fuse_relu_ = false, fuse_mask_ = false;
 };
 
 class EdgeWithWeight : public Edge {
@@ -128,6 +137,8 @@ class ConvEdge : public EdgeWithWeight {
   double FlopsUp() const override;
   int FanIn() const override;
   ConvDesc GetConvDesc() const { return conv_desc_; }
+  bool CanFuseReLU() const override { return !has_no_bias_ && shared_bias_ && image_size_t_ == 1; }
+  bool CanFuseMask() const override { return image_size_t_ == 1; }
 
  private:
   ConvDesc conv_desc_;
@@ -147,6 +158,8 @@ class FCEdge : public EdgeWithWeight {          // weights [Cout x K] column-maj
   void ComputeOuter(Matrix& input, Matrix& deriv_output) override;
   double FlopsUp() const override;
   int FanIn() const override { return num_inputs_; }
+  bool CanFuseReLU() const override { return !has_no_bias_; }
+  bool CanFuseMask() const override { return true; }
 
  private:
   void View(Matrix& in, Matrix& out);
@@ -166,6 +179,8 @@ class ConvOneToOneEdge : public EdgeWithWeight {
   void ComputeOuter(Matrix& input, Matrix& deriv_output) override;
   double FlopsUp() const override;
   int FanIn() const override { return num_input_channels_; }
+  bool CanFuseReLU() const override { return !has_no_bias_; }
+  bool CanFuseMask() const override { return true; }
 
  private:
   ConvDesc desc_;
@@ -177,6 +192,7 @@ class MaxPoolEdge : public Edge {
   void SetImageSize(int y, int x, int t) override;
   void ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) override;
   void ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) override;
+  bool CanFuseMask() const override { return true; }
 
  protected:
   ConvDesc conv_desc_;

@@ -71,6 +71,7 @@ SIGNATURES = {
     "convnet_b200_get_conv_precision": [],
     "convnet_b200_last_conv_path": [],
     "convnet_b200_launch_count": [],
+    "convnet_b200_fuse_next": [FP, I, FP],
     "convnet_b200_reset_launch_count": [],
     "convnet_b200_release_workspace": [],
     "cnb_add_channel_bias": [FP, FP, ct.c_longlong, I],

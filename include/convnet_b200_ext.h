@@ -45,6 +45,15 @@ void convnet_b200_reset_launch_count(void);
 /* Free cached device scratch (wgrad partial sums).  Never required. */
 void convnet_b200_release_workspace(void);
 
+/* One-shot epilogue fusion for the NEXT conv / pool-undo call of this library (cleared by that call):
+ *   bias      (convUp*, localUp excluded): adds bias[o] to every output of output channel o — the shared-bias
+ *             AddRowVec of ConvEdge::ComputeUp (src/conv_edge.cc:143-152) without the extra pass;
+ *   relu      (convUp*): clamps at 0 after the bias — Layer::ApplyActivation for RECTIFIED_LINEAR (src/layer.cc:550);
+ *   relu_mask (convDown*, MaxPoolUndo*, AvgPoolUndo*): result zeroed where relu_mask[i] <= 0; relu_mask has the shape
+ *             of `targets` (it is the state of the layer receiving the derivative: ApplyDerivativeOfActivation).
+ * Pass NULL / 0 for the parts not wanted.  Calls that cannot fuse (3-D dgrad) apply the same maths in a second pass. */
+void convnet_b200_fuse_next(const float* bias, int relu, const float* relu_mask);
+
 /* ---- steps either side of the conv ops that the Edge layer sequences ------------
  * (in the reference these are libcudamat.so calls:
  *  add_row_vec cudamat.cu:1064, sum_by_axis :1614, lower_bound_scalar :1426,

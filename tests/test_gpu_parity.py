@@ -469,3 +469,43 @@ def test_elementwise_helpers(gpu):
     h2 = 0.9 * h + 0.01 * (g_ + 5e-4 * w); w2 = w - h2
     L.cnb_sgd_momentum(w.data_ptr(), h.data_ptr(), g_.data_ptr(), 1001, 0.01, 0.9, 5e-4)
     assert torch.allclose(w, w2, atol=1e-6) and torch.allclose(h, h2, atol=1e-6)
+
+
+@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+def test_fused_epilogues(gpu, oracle, mode):
+    """convnet_b200_fuse_next: bias + ReLU in the fprop epilogue, ReLU' mask in dgrad / pool-undo epilogues must equal the
+    unfused sequence (conv -> AddRowVec -> LowerBound(0); conv -> ApplyDerivativeOfActivation)."""
+    torch = gpu.torch
+    gpu.lib.set_precision(mode)
+    L = gpu.lib.load()
+    d, ish, fsh, tsh, images, filters, derivs = _conv_case((128, 10, 10, 32, 64, 3, 3, 1, 1, 1, 1))
+    N = ish[0]
+    gi, gf, gd = gpu.up(images, ish), gpu.up(filters, fsh), gpu.up(derivs, tsh)
+    r = np.random.RandomState(4)
+    bias = torch.from_numpy(r.randn(64).astype(np.float32)).cuda()
+    # fprop: bias + relu
+    ref = Z(*derivs.shape); oracle.convUp(images, filters, ref, ish, fsh, tsh, d)
+    ref = np.maximum(ref.reshape(N, 64, 100) + bias.cpu().numpy()[None, :, None], 0).reshape(N, -1)   # cols = mod + 100*o
+    out = gpu.nan(N, derivs.shape[1], tsh)
+    L.convnet_b200_fuse_next(bias.data_ptr(), 1, None); gpu.cg.convUp(gi, gf, out, d)
+    assert Diff(out.asarray(), ref) < TOL[mode]
+    out2 = gpu.nan(N, derivs.shape[1], tsh); gpu.cg.convUp(gi, gf, out2, d)      # the request was one-shot
+    assert (out2.asarray() < 0).any()
+    # dgrad: mask
+    state = F(r.randn(*images.shape)); gs = gpu.up(state, ish)
+    ref = Z(*images.shape); oracle.convDown(derivs, filters, ref, tsh, fsh, ish, d)
+    ref = np.where(state > 0, ref, 0).astype(np.float32)
+    out = gpu.nan(*images.shape, ish)
+    L.convnet_b200_fuse_next(None, 0, gs.ptr); gpu.cg.convDown(gd, gf, out, d)
+    assert Diff(out.asarray(), ref) < TOL[mode]
+    # max-pool undo: mask
+    pd = GetConvDesc(32, 32, 3, 3, 2, 2, 1, 1)
+    psh = (N, 5, 5, 32)
+    pim = F(r.rand(*images.shape)); gpim = gpu.up(pim, ish)
+    grads = F(r.randn(N, 25 * 32)); gg = gpu.up(grads, psh)
+    mx = gpu.nan(N, 25 * 32, psh); gpu.cg.MaxPool(gpim, mx, pd)
+    ref = Z(*images.shape); oracle.maxPoolUndo(pim, grads, mx.asarray(), ref, ish, psh, pd)
+    ref = np.where(state > 0, ref, 0).astype(np.float32)
+    out = gpu.nan(*images.shape, ish)
+    L.convnet_b200_fuse_next(None, 0, gs.ptr); gpu.cg.MaxPoolUndo(gpim, gg, mx, out, pd)
+    assert Diff(out.asarray(), ref) < TOL_MEM
