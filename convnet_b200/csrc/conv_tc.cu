@@ -461,16 +461,27 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         } else if (fused) {
           float* dst = row_ptr + col_stride * j0;
-          const float* bias = (OP == kFprop && p.bias) ? p.bias + tile.n_tile * p.BN + j0 : nullptr;
+          // all 32 auxiliary loads (bias values / mask elements) are issued before the first dependent store;
+          // interleaving them with the stores serialised one memory latency per column
+          float aux[32];
+          if (OP == kFprop) {
+            const float* bias = p.bias ? p.bias + tile.n_tile * p.BN + j0 : nullptr;
+#pragma unroll
+            for (int j = 0; j < 32; j++) aux[j] = (bias != nullptr && j < nv) ? __ldg(bias + j) : 0.f;
+          } else {
+            const float* mp = p.mask + (dst - p.out);
+#pragma unroll
+            for (int j = 0; j < 32; j++) aux[j] = (j < nv) ? __ldg(mp + col_stride * j) : 1.f;
+          }
 #pragma unroll
           for (int j = 0; j < 32; j++, dst += col_stride)
             if (j < nv) {
               float r = so_eff * v[j];
               if (rmw) r += p.st * (*dst);
               if (OP == kFprop) {
-                if (bias) r += __ldg(bias + j);
+                r += aux[j];
                 if (p.relu) r = fmaxf(r, 0.f);
-              } else if (!(__ldg(p.mask + (dst - p.out)) > 0.f)) r = 0.f;
+              } else if (!(aux[j] > 0.f)) r = 0.f;
               *dst = r;
             }
         } else if (rmw) {
