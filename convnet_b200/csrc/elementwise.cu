@@ -73,13 +73,25 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* out, 
   out[c] = (st == 0.f) ? so * s : st * out[c] + so * s;
 }
 
-__global__ void relu_kernel(float* x, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    x[i] = fmaxf(x[i], 0.f);
+// n4 = number of float4 groups (vector body); the scalar tail [4*n4, n) is handled by the same launch
+__global__ void relu_kernel(float* x, long long n, long long n4) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n4; i += nt) {
+    float4 v = reinterpret_cast<float4*>(x)[i];
+    v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
+    reinterpret_cast<float4*>(x)[i] = v;
+  }
+  for (long long i = 4 * n4 + tid; i < n; i += nt) x[i] = fmaxf(x[i], 0.f);
 }
-__global__ void relu_deriv_kernel(float* dx, const float* __restrict__ y, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
-    dx[i] = y[i] > 0.f ? dx[i] : 0.f;
+__global__ void relu_deriv_kernel(float* dx, const float* __restrict__ y, long long n, long long n4) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n4; i += nt) {
+    float4 d = reinterpret_cast<float4*>(dx)[i];
+    const float4 s = __ldg(reinterpret_cast<const float4*>(y) + i);
+    d.x = s.x > 0.f ? d.x : 0.f; d.y = s.y > 0.f ? d.y : 0.f; d.z = s.z > 0.f ? d.z : 0.f; d.w = s.w > 0.f ? d.w : 0.f;
+    reinterpret_cast<float4*>(dx)[i] = d;
+  }
+  for (long long i = 4 * n4 + tid; i < n; i += nt) dx[i] = y[i] > 0.f ? dx[i] : 0.f;
 }
 __global__ void sgd_kernel(float* w, float* h, const float* __restrict__ g, long long n, float lr, float mom, float l2) {
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -102,8 +114,15 @@ __global__ void dropout_kernel(float* x, float* mask, long long n, float droppro
     x[i] *= m;
   }
 }
-__global__ void mult_kernel(float* a, const float* __restrict__ b, long long n) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) a[i] *= b[i];
+__global__ void mult_kernel(float* a, const float* __restrict__ b, long long n, long long n4) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n4; i += nt) {
+    float4 x = reinterpret_cast<float4*>(a)[i];
+    const float4 m = __ldg(reinterpret_cast<const float4*>(b) + i);
+    x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+    reinterpret_cast<float4*>(a)[i] = x;
+  }
+  for (long long i = 4 * n4 + tid; i < n; i += nt) a[i] *= b[i];
 }
 
 // softmax over classes of a column-major [rows x cols] matrix: one block per 32 images; lane = image (coalesced
@@ -174,12 +193,14 @@ void cnb_channel_bias_grad(const float* derivs, float* grad_bias, long long rows
 }
 void cnb_relu(float* x, long long n) {
   if (n <= 0) return;
-  relu_kernel<<<blocks_for(n, 256), 256, 0, state().stream>>>(x, n);
+  const long long n4 = aligned16(x) ? n / 4 : 0;
+  relu_kernel<<<blocks_for(std::max(n4, n - 4 * n4), 256), 256, 0, state().stream>>>(x, n, n4);
   count_launch(); CNB_LAUNCH_CHECK("relu");
 }
 void cnb_relu_deriv(float* dx, const float* y, long long n) {
   if (n <= 0) return;
-  relu_deriv_kernel<<<blocks_for(n, 256), 256, 0, state().stream>>>(dx, y, n);
+  const long long n4 = (aligned16(dx) && aligned16(y)) ? n / 4 : 0;
+  relu_deriv_kernel<<<blocks_for(std::max(n4, n - 4 * n4), 256), 256, 0, state().stream>>>(dx, y, n, n4);
   count_launch(); CNB_LAUNCH_CHECK("relu_deriv");
 }
 void cnb_dropout(float* x, float* mask, long long n, float dropprob, float scale, unsigned long long seed) {
@@ -189,7 +210,8 @@ void cnb_dropout(float* x, float* mask, long long n, float dropprob, float scale
 }
 void cnb_mult(float* a, const float* b, long long n) {
   if (n <= 0) return;
-  mult_kernel<<<blocks_for(n, 256), 256, 0, state().stream>>>(a, b, n);
+  const long long n4 = (aligned16(a) && aligned16(b)) ? n / 4 : 0;
+  mult_kernel<<<blocks_for(std::max(n4, n - 4 * n4), 256), 256, 0, state().stream>>>(a, b, n, n4);
   count_launch(); CNB_LAUNCH_CHECK("mult");
 }
 void cnb_softmax(float* x, int rows, int cols) {

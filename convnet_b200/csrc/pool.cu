@@ -34,15 +34,15 @@ template <> __device__ __forceinline__ void vstore<1>(float* p, const float (&v)
 template <int VEC, bool MAX, int K>
 __global__ void __launch_bounds__(256) pool_fwd_kernel(PoolGeom g, const float* __restrict__ images,
                                                         float* __restrict__ targets, float so, long long total) {
-  const int NV = g.N / VEC;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int nv = (int)(idx % NV);
-    long long r = idx / NV;
-    const int mx = (int)(r % g.modX); r /= g.modX;
-    const int my = (int)(r % g.modY); r /= g.modY;
-    const int c = (int)(r % g.C);
-    const int mt = (int)(r / g.C);
+  // blockIdx.y = (channel, output frame) plane; inside a plane all index arithmetic is 32-bit (the 64-bit
+  // divisions of a flat index made these kernels instruction-bound, not HBM-bound)
+  const unsigned NV = g.N / VEC;
+  const unsigned plane = NV * g.modX * g.modY;                   // `total` = elements per plane
+  const int c = blockIdx.y % g.C, mt = blockIdx.y / g.C;
+  for (unsigned pidx = blockIdx.x * blockDim.x + threadIdx.x; pidx < plane; pidx += gridDim.x * blockDim.x) {
+    const unsigned nv = pidx % NV, r = pidx / NV;
+    const int mx = r % g.modX, my = r / g.modX;
+    const long long idx = (long long)blockIdx.y * plane + pidx;
     float acc[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; v++) acc[v] = MAX ? -2e38f : 0.f;     // base value: gemm.cu:71
@@ -110,15 +110,13 @@ __global__ void __launch_bounds__(256) pool_undo_kernel(PoolGeom g, const float*
                                                          const float* __restrict__ acts, float* targets,
                                                          float st, float so, long long total,
                                                          const float* __restrict__ relu_mask) {
-  const int NV = g.N / VEC;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int nv = (int)(idx % NV);
-    long long r = idx / NV;
-    const int X = (int)(r % g.W); r /= g.W;
-    const int Y = (int)(r % g.H); r /= g.H;
-    const int c = (int)(r % g.C);
-    const int T = (int)(r / g.C);
+  const unsigned NV = g.N / VEC;
+  const unsigned plane = NV * g.W * g.H;
+  const int c = blockIdx.y % g.C, T = blockIdx.y / g.C;
+  for (unsigned pidx = blockIdx.x * blockDim.x + threadIdx.x; pidx < plane; pidx += gridDim.x * blockDim.x) {
+    const unsigned nv = pidx % NV, r = pidx / NV;
+    const int X = r % g.W, Y = r / g.W;
+    const long long idx = (long long)blockIdx.y * plane + pidx;
     int x0, x1, y0, y1, t0, t1;
     cover(X, g.sx, g.px, g.kx, g.modX, x0, x1);
     cover(Y, g.sy, g.py, g.ky, g.modY, y0, y1);
@@ -187,14 +185,19 @@ __global__ void __launch_bounds__(256) pool_undo_kernel(PoolGeom g, const float*
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int grid_for(long long total) {
+  static int mult = 0;
+  if (!mult) { const char* e = getenv("CONVNET_B200_POOL_GRID_MULT"); mult = e ? atoi(e) : 16; if (mult < 1) mult = 16; }
   const long long want = ceil_div<long long>(total, 256);
-  return (int)std::min<long long>(want, (long long)num_sms() * 16);   // multiple of the SM count when large
+  return (int)std::min<long long>(want, (long long)num_sms() * mult);   // multiple of the SM count when large
 }
 
 template <int VEC, bool MAX>
 static void launch_fwd(const PoolGeom& g, const float* images, float* targets, float so, long long total) {
   cudaStream_t s = state().stream;
-  const int grid = grid_for(total);
+  const int planes = g.C * g.modT;
+  const long long per_plane = total / planes;
+  CNB_REQUIRE(per_plane < (1LL << 31) && planes <= 65535, "pool_forward: plane too large");
+  const dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(ceil_div<long long>(per_plane, 256), 64)), planes);
   const int k = (g.kt == 1 && g.T == 1 && g.modT == 1) ? std::max(g.kx, g.ky) : 99;
   if (k <= 2) pool_fwd_kernel<VEC, MAX, 2><<<grid, 256, 0, s>>>(g, images, targets, so, total);
   else if (k == 3) pool_fwd_kernel<VEC, MAX, 3><<<grid, 256, 0, s>>>(g, images, targets, so, total);
@@ -220,7 +223,10 @@ template <int VEC, bool MAX>
 static void launch_undo(const PoolGeom& g, const float* images, const float* grads, const float* acts, float* targets,
                         float st, float so, long long total, const float* mask) {
   cudaStream_t s = state().stream;
-  const int grid = grid_for(total);
+  const int planes = g.C * g.T;
+  const long long per_plane = total / planes;
+  CNB_REQUIRE(per_plane < (1LL << 31) && planes <= 65535, "pool_undo: plane too large");
+  const dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(ceil_div<long long>(per_plane, 256), 64)), planes);
   // windows covering one element per axis: ceil(k / stride)
   const int q = (g.kt == 1 && g.T == 1 && g.modT == 1) ? std::max(ceil_div(g.kx, g.sx), ceil_div(g.ky, g.sy)) : 99;
   if (q <= 1) pool_undo_kernel<VEC, MAX, 1><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total, mask);

@@ -54,6 +54,7 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_fwd_kernel(const float* __re
   // q = entering channel; output channel j = q - b; window [j-a, j+b] = [q-k+1, q].
   // Loads are hoisted eight steps ahead of the (serial) ring updates to keep HBM requests in flight.
   const int q0 = max(0, f0 - a), q1 = f1 + b;      // channels >= F enter as zeros
+  int slot_q = q0 % k, slot_j = ((q0 - b) % k + k) % k;           // ring slots of q and of j = q - b, advanced with wrap
   for (int qb = q0; qb < q1; qb += 8) {
     float xv[8];
 #pragma unroll
@@ -62,7 +63,7 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_fwd_kernel(const float* __re
     for (int u = 0; u < 8; u++) {
       const int q = qb + u;
       if (q >= q1) break;
-      const int slot = q % k;
+      const int slot = slot_q;
       const float v = xv[u];
       float old = 0.f;
       if (q - q0 >= k) old = ring[slot * rs];
@@ -70,9 +71,11 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_fwd_kernel(const float* __re
       sum += v * v - old * old;
       const int j = q - b;
       if (j >= f0 && j < f1) {
-        const float xj = (j == q) ? v : ring[(j % k) * rs];
+        const float xj = (j == q) ? v : ring[slot_j * rs];
         y[(long long)j * L] = xj * __powf(1.f + alpha * sum, -beta);
       }
+      if (++slot_q == k) slot_q = 0;
+      if (++slot_j == k) slot_j = 0;
     }
   }
 }
@@ -113,6 +116,8 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_undo_kernel(const float* __r
   const int q0 = max(0, f0 - (k - 1));                   // first x needed: (f0 - b) - a
   const int i0 = max(0, f0 - b);                         // first t needed
   const int Qend = f1 + a + b;                           // last output f1-1 needs t up to f1-1+a, i.e. q up to f1-1+a+b
+  // ring slots of q, i = q - b and j = i - a, advanced with wrap instead of three `% k` per channel
+  int slot_q = q0 % k, slot_i = ((q0 - b) % k + k) % k, slot_j = ((q0 - b - a) % k + k) % k;
   for (int qb = q0; qb < Qend; qb += 4) {
     float xv[4], gv[4];
 #pragma unroll
@@ -125,8 +130,12 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_undo_kernel(const float* __r
     for (int u = 0; u < 4; u++) {
       const int q = qb + u;
       if (q >= Qend) break;
+      const int sq = slot_q, si = slot_i, sj = slot_j;
+      if (++slot_q == k) slot_q = 0;
+      if (++slot_i == k) slot_i = 0;
+      if (++slot_j == k) slot_j = 0;
       {
-        const int slot = q % k;
+        const int slot = sq;
         const float v = xv[u];
         float old = 0.f;
         if (q - q0 >= k) old = rx[slot * rs];
@@ -136,7 +145,7 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_undo_kernel(const float* __r
       const int i = q - b;
       if (i < i0) continue;
       {
-        const int slot = i % k;
+        const int slot = si;
         float told = 0.f, t = 0.f;
         if (i - i0 >= k) told = rt[slot * rs];
         if (i < F) {
@@ -151,7 +160,7 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_undo_kernel(const float* __r
       }
       const int j = i - a;
       if (j >= f0 && j < f1) {
-        const int slot = j % k;
+        const int slot = sj;
         dx[(long long)j * L] = rp[slot * rs] - c2 * rx[slot * rs] * sumt;
       }
     }
