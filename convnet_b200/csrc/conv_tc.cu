@@ -54,6 +54,11 @@ struct TcParams {
   // merged requests: when N % 128 == 0 (2-D) the four 32-image chunks of an m-tile are one box over a
   // (32, ..., N/32, ...) view of the tensor; when Cout % 32 == 0 the BN/32 filter chunks are one box likewise.
   int a_merged, b_merged;
+  // CTA pairs (tcgen05 cta_group::2): two CTAs of a cluster share one 256 x BN tile; each loads its own 128 rows of A
+  // and HALF of B, the leader issues M = 256 MMAs that read both shared memories, each CTA keeps its 128 rows in TMEM.
+  int cta2;
+  int dbg;                          // CONVNET_B200_TC_DEBUG bits (timing experiments only): 1 = no TMA loads, 2 = no MMAs
+  int m_groups;                     // m-tiles (or o-tiles) per scheduling unit: m_tiles, or ceil(m_tiles/2) with cta2
   int total_chunks;                 // fprop: nb*modules*frames ; dgrad: nb*W*H   (< 2^31, checked on the host)
   int splits, units_per_split;      // wgrad: (frame, module-row) units per reduction split
   float* out;
@@ -82,17 +87,19 @@ struct Tile {
 };
 
 template <int OP>
-__device__ __forceinline__ Tile decode_tile(const TcParams& p, int t) {
+__device__ __forceinline__ Tile decode_tile(const TcParams& p, int t, int rank) {
   Tile r;
   if (OP == kWgrad) {
     r.split = t % p.splits; t /= p.splits;
     r.c_tile = t % p.n_tiles; t /= p.n_tiles;
-    r.o_tile = t % p.m_tiles; t /= p.m_tiles;
+    r.o_tile = t % p.m_groups; t /= p.m_groups;
+    if (p.cta2) r.o_tile = 2 * r.o_tile + rank;
     r.tap = t;
     r.m_tile = r.o_tile; r.n_tile = r.c_tile;
   } else {
     r.n_tile = t % p.n_tiles;
     r.m_tile = t / p.n_tiles;
+    if (p.cta2) r.m_tile = 2 * r.m_tile + rank;
     r.tap = r.o_tile = r.c_tile = r.split = 0;
   }
   return r;
@@ -144,10 +151,10 @@ __device__ __forceinline__ DgradTaps dgrad_taps(const TcParams& p, const Chunks&
   }
   return d;
 }
-__device__ __forceinline__ int dgrad_live_taps(const TcParams& p, const DgradTaps& d) {
+__device__ __forceinline__ int dgrad_live_taps(const TcParams& p, const DgradTaps& d, const DgradTaps& e) {
   int live = 0;
   for (int ty = 0; ty < p.ky; ty++)
-    for (int tx = 0; tx < p.kx; tx++) live += d.any(tx, ty) ? 1 : 0;
+    for (int tx = 0; tx < p.kx; tx++) live += (d.any(tx, ty) || e.any(tx, ty)) ? 1 : 0;
   return live;
 }
 
@@ -174,12 +181,17 @@ __device__ __forceinline__ WgradSpan wgrad_span(const TcParams& p, const Tile& t
 }
 
 // ------------------------------------------------------------------------------------------------
-template <int OP>
+// PAIR kernels hold only cta_group::2 tcgen05 instructions and MUST be launched as clusters of two (the driver rejects
+// a kernel that uses cta_group::2 outside a cluster launch, so the two flavours are separate instantiations).
+template <int OP, bool PAIR>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const uint32_t b_stage_bytes = (uint32_t)p.BN * BK * 4;
+  constexpr bool cta2 = PAIR;
+  const int rank = cta2 ? (int)ptx::cluster_ctarank() : 0;          // 0 = leader of the pair
+  const int bn_local = cta2 ? p.BN / 2 : p.BN;                      // B columns / rows this CTA stages
+  const uint32_t b_stage_bytes = (uint32_t)bn_local * BK * 4;
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + (size_t)p.stages * kAStageBytes;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smemB + (size_t)p.stages * b_stage_bytes);
@@ -188,28 +200,50 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; s++) { ptx::mbar_init(&ctl->full[s], 1); ptx::mbar_init(&ctl->empty[s], 1); }
-    for (int a = 0; a < 2; a++) { ptx::mbar_init(&ctl->tmem_full[a], 1); ptx::mbar_init(&ctl->tmem_empty[a], 4); }
+    for (int a = 0; a < 2; a++) { ptx::mbar_init(&ctl->tmem_full[a], 1); ptx::mbar_init(&ctl->tmem_empty[a], cta2 ? 8 : 4); }
     ptx::fence_barrier_init();
     ptx::tma_prefetch_desc(&mapA);
     ptx::tma_prefetch_desc(&mapB);
   }
-  if (warp == 1) { ptx::tmem_alloc(&ctl->tmem_base, (uint32_t)p.tmem_cols); ptx::tmem_relinquish(); }
+  if (warp == 1) {
+    if constexpr (cta2) { ptx::tmem_alloc_2sm(&ctl->tmem_base, (uint32_t)p.tmem_cols); ptx::tmem_relinquish_2sm(); }
+    else { ptx::tmem_alloc(&ctl->tmem_base, (uint32_t)p.tmem_cols); ptx::tmem_relinquish(); }
+  }
   ptx::tc_fence_before();
-  __syncthreads();
+  if constexpr (cta2) ptx::cluster_sync(); else __syncthreads();              // peer barriers are initialised before anyone signals them
   ptx::tc_fence_after();
+  const int t_first = cta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = cta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t tmem_base = ctl->tmem_base;
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
-      const uint32_t tx_bytes = kAStageBytes + p.b_tx_bytes;
-      for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-        const Tile tile = decode_tile<OP>(p, t);
+      const bool no_tma = (p.dbg & 1) != 0;
+      const uint32_t tx_bytes = no_tma ? 0u : (kAStageBytes + p.b_tx_bytes) * (cta2 ? 2u : 1u);   // the leader's barrier counts both CTAs
+      for (int t = t_first; t < p.num_tiles; t += t_step) {
+        const Tile tile = decode_tile<OP>(p, t, rank);
         auto begin_stage = [&]() -> uint8_t* {
           ptx::mbar_wait(&ctl->empty[stage], phase ^ 1);
-          ptx::mbar_arrive_expect_tx(&ctl->full[stage], tx_bytes);
+          if (rank == 0) ptx::mbar_arrive_expect_tx(&ctl->full[stage], tx_bytes);
           return smemA + (size_t)stage * kAStageBytes;
+        };
+        // TMA wrappers: in pair mode the completion bytes go to the leader's barrier
+        auto lda5 = [&](const void* m, void* dst, int c0, int c1, int c2, int c3, int c4) {
+          if (no_tma) return;
+          if constexpr (cta2) ptx::tma_load_5d_2sm(m, &ctl->full[stage], dst, c0, c1, c2, c3, c4);
+          else ptx::tma_load_5d(m, &ctl->full[stage], dst, c0, c1, c2, c3, c4);
+        };
+        auto lda4 = [&](const void* m, void* dst, int c0, int c1, int c2, int c3) {
+          if (no_tma) return;
+          if constexpr (cta2) ptx::tma_load_4d_2sm(m, &ctl->full[stage], dst, c0, c1, c2, c3);
+          else ptx::tma_load_4d(m, &ctl->full[stage], dst, c0, c1, c2, c3);
+        };
+        auto lda3 = [&](const void* m, void* dst, int c0, int c1, int c2) {
+          if (no_tma) return;
+          if constexpr (cta2) ptx::tma_load_3d_2sm(m, &ctl->full[stage], dst, c0, c1, c2);
+          else ptx::tma_load_3d(m, &ctl->full[stage], dst, c0, c1, c2);
         };
         auto end_stage = [&]() { if (++stage == p.stages) { stage = 0; phase ^= 1; } };
 
@@ -249,17 +283,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 uint8_t* a = begin_stage();
                 uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
                 if (p.a_merged) {                // dims (n_lo, c, n_hi, x, y): one 16 KiB request
-                  ptx::tma_load_5d(&mapA, &ctl->full[stage], a, 0, cb * BK, ch.n[0] >> 5, cX[0] + tx, cY[0] + ty);
+                  lda5(&mapA, a, 0, cb * BK, ch.n[0] >> 5, cX[0] + tx, cY[0] + ty);
                 } else {
 #pragma unroll
                   for (int c = 0; c < 4; c++)
-                    ptx::tma_load_5d(&mapA, &ctl->full[stage], a + c * (BK * 128), ch.n[c], cb * BK, cX[c] + tx, cY[c] + ty, ch.f[c]);
+                    lda5(&mapA, a + c * (BK * 128), ch.n[c], cb * BK, cX[c] + tx, cY[c] + ty, ch.f[c]);
                 }
+                const int o0 = tile.n_tile * p.BN + rank * bn_local;      // this CTA's share of the filter columns
                 if (p.b_merged) {                // dims (o_lo, c, o_hi, tap)
-                  ptx::tma_load_4d(&mapB, &ctl->full[stage], b, 0, cb * BK, tile.n_tile * (p.BN >> 5), tap);
+                  lda4(&mapB, b, 0, cb * BK, o0 >> 5, tap);
                 } else {
-                  for (int j = 0; j < p.BN / 32; j++)
-                    ptx::tma_load_3d(&mapB, &ctl->full[stage], b + j * (BK * 128), tile.n_tile * p.BN + j * 32, tap, cb * BK);
+                  for (int j = 0; j < bn_local / 32; j++)
+                    lda3(&mapB, b + j * (BK * 128), o0 + j * 32, tap, cb * BK);
                 }
                 end_stage();
               }
@@ -267,13 +302,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         } else if (OP == kDgrad) {
           const Chunks ch = decode_chunks(p, tile.m_tile, p.W * p.H);
           const DgradTaps taps = dgrad_taps(p, ch);
-          const bool none = dgrad_live_taps(p, taps) == 0;       // then one all-zero k-block keeps the pipeline uniform
+          // the pair walks the UNION of the two m-tiles' live taps (a tap dead for this CTA loads zeros)
+          const DgradTaps peer = cta2 ? dgrad_taps(p, decode_chunks(p, tile.m_tile ^ 1, p.W * p.H)) : taps;
+          const bool none = dgrad_live_taps(p, taps, peer) == 0;  // then one all-zero k-block keeps the pipeline uniform
           int cX[4], cY[4];
 #pragma unroll
           for (int c = 0; c < 4; c++) { cX[c] = ch.pos[c] % p.W; cY[c] = ch.pos[c] / p.W; }
           for (int ty = 0; ty < p.ky; ty++)
             for (int tx = 0; tx < p.kx; tx++) {
-              if (!(taps.any(tx, ty) || (none && tx == 0 && ty == 0))) continue;
+              if (!(taps.any(tx, ty) || peer.any(tx, ty) || (none && tx == 0 && ty == 0))) continue;
               int mx[4], my[4];
 #pragma unroll
               for (int c = 0; c < 4; c++) {
@@ -286,13 +323,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 uint8_t* a = begin_stage();
                 uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
                 if (p.a_merged) {                // all four chunks sit on the same pixel: dims (n_lo, o, n_hi, mx, my)
-                  ptx::tma_load_5d(&mapA, &ctl->full[stage], a, 0, ob * BK, ch.n[0] >> 5, mx[0], my[0]);
+                  lda5(&mapA, a, 0, ob * BK, ch.n[0] >> 5, mx[0], my[0]);
                 } else {
 #pragma unroll
                   for (int c = 0; c < 4; c++)
-                    ptx::tma_load_5d(&mapA, &ctl->full[stage], a + c * (BK * 128), ch.n[c], ob * BK, mx[c], my[c], p.frame0);
+                    lda5(&mapA, a + c * (BK * 128), ch.n[c], ob * BK, mx[c], my[c], p.frame0);
                 }
-                ptx::tma_load_3d(&mapB, &ctl->full[stage], b, ob * BK, tap, tile.n_tile * p.BN);
+                lda3(&mapB, b, ob * BK, tap, tile.n_tile * p.BN + rank * bn_local);
                 end_stage();
               }
             }
@@ -320,8 +357,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             for (int ib = 0; ib < p.nb; ib++) {
               uint8_t* a = begin_stage();
               uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
-              ptx::tma_load_5d(&mapA, &ctl->full[stage], a, ib * 32, 0, 0, tile.o_tile * BM, 0);
-              ptx::tma_load_5d(&mapB, &ctl->full[stage], b, ib * 32, -1, -1, tile.c_tile * p.BN, 0);
+              lda5(&mapA, a, ib * 32, 0, 0, tile.o_tile * BM, 0);
+              lda5(&mapB, b, ib * 32, -1, -1, tile.c_tile * p.BN + rank * bn_local, 0);
               end_stage();
             }
           } else {
@@ -334,8 +371,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 for (int ib = 0; ib < p.nb; ib++) {
                   uint8_t* a = begin_stage();
                   uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
-                  ptx::tma_load_5d(&mapA, &ctl->full[stage], a, ib * 32, mx, my, tile.o_tile * BM, f);
-                  ptx::tma_load_5d(&mapB, &ctl->full[stage], b, ib * 32, X, Y, tile.c_tile * p.BN, f);
+                  lda5(&mapA, a, ib * 32, mx, my, tile.o_tile * BM, f);
+                  lda5(&mapB, b, ib * 32, X, Y, tile.c_tile * p.BN + rank * bn_local, f);
                   end_stage();
                 }
               }
@@ -344,8 +381,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         }
       }
     }
-  } else if (warp == 1) {
-    // =============================== MMA issuer =================================
+  } else if (warp == 1 && rank == 0) {
+    // =============================== MMA issuer (leader CTA only in pair mode) ===
     int stage = 0; uint32_t phase = 0;
     int acc = 0; uint32_t acc_phase = 0;
     // operand descriptors.
@@ -358,14 +395,15 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     const uint32_t a_lay = a_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
     const uint32_t b_lay = b_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
     const uint32_t a_kstep = a_mn ? 1024 : 32, b_kstep = b_mn ? 1024 : 32;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const Tile tile = decode_tile<OP>(p, t);
+    for (int t = t_first; t < p.num_tiles; t += t_step) {
+      const Tile tile = decode_tile<OP>(p, t, rank);
       int nkb;
       if (OP == kFprop) {
         nkb = p.x_mode ? p.Cin * p.x_yblocks : p.taps * p.kc_blocks;
       } else if (OP == kDgrad) {
-        const Chunks ch = decode_chunks(p, tile.m_tile, p.W * p.H);
-        nkb = max(dgrad_live_taps(p, dgrad_taps(p, ch)), 1) * p.kc_blocks;
+        const DgradTaps own = dgrad_taps(p, decode_chunks(p, tile.m_tile, p.W * p.H));
+        const DgradTaps peer = cta2 ? dgrad_taps(p, decode_chunks(p, tile.m_tile ^ 1, p.W * p.H)) : own;
+        nkb = max(dgrad_live_taps(p, own, peer), 1) * p.kc_blocks;
       } else if (p.x_mode) {
         const int r0 = tile.split * p.units_per_split, r1 = min(r0 + p.units_per_split, p.modY * p.frames);
         nkb = (r1 - r0) * p.modX * p.nb;
@@ -380,28 +418,36 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         ptx::mbar_wait(&ctl->full[stage], phase);
         ptx::tc_fence_after();
         if (lane == 0) {
+          if (!(p.dbg & 2)) {
           const uint32_t a_addr = ptx::smem_u32(smemA + (size_t)stage * kAStageBytes);
           const uint32_t b_addr = ptx::smem_u32(smemB + (size_t)stage * b_stage_bytes);
 #pragma unroll
           for (int ks = 0; ks < BK / 8; ks++) {
             const uint64_t da = ptx::make_smem_desc(a_addr + ks * a_kstep, a_lbo, a_sbo, a_lay);
             const uint64_t db = ptx::make_smem_desc(b_addr + ks * b_kstep, b_lbo, b_sbo, b_lay);
-            ptx::mma_tf32(d_tmem, da, db, p.idesc, (kb | ks) != 0);
+            if constexpr (cta2) ptx::mma_tf32_2sm(d_tmem, da, db, p.idesc, (kb | ks) != 0);
+            else ptx::mma_tf32(d_tmem, da, db, p.idesc, (kb | ks) != 0);
           }
-          ptx::mma_commit(&ctl->empty[stage]);              // frees the smem slot when these MMAs retire
-          if (kb == nkb - 1) ptx::mma_commit(&ctl->tmem_full[acc]);
+          }
+          if constexpr (cta2) {                                       // frees the slot / publishes the accumulator in BOTH CTAs
+            ptx::mma_commit_2sm(&ctl->empty[stage], 3);
+            if (kb == nkb - 1) ptx::mma_commit_2sm(&ctl->tmem_full[acc], 3);
+          } else {
+            ptx::mma_commit(&ctl->empty[stage]);            // frees the smem slot when these MMAs retire
+            if (kb == nkb - 1) ptx::mma_commit(&ctl->tmem_full[acc]);
+          }
         }
         __syncwarp();
         if (++stage == p.stages) { stage = 0; phase ^= 1; }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-  } else {
+  } else if (warp >= 2) {
     // =============================== epilogue ===================================
     const int quarter = warp & 3;                      // TMEM lane quarter this warp may read
     int acc = 0; uint32_t acc_phase = 0;
-    for (int t = blockIdx.x; t < p.num_tiles; t += gridDim.x) {
-      const Tile tile = decode_tile<OP>(p, t);
+    for (int t = t_first; t < p.num_tiles; t += t_step) {
+      const Tile tile = decode_tile<OP>(p, t, rank);
       // row owned by this thread and the address of its column 0
       float* row_ptr = nullptr;
       long long col_stride = 0;
@@ -498,14 +544,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       }
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&ctl->tmem_empty[acc]);
+      if (lane == 0) {                                     // the leader's MMA warp owns the accumulator hand-shake
+        if (rank == 0) ptx::mbar_arrive(&ctl->tmem_empty[acc]);
+        else ptx::mbar_arrive_remote(&ctl->tmem_empty[acc], 0);
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
   }
 
   ptx::tc_fence_before();
-  __syncthreads();
-  if (warp == 1) { ptx::tc_fence_after(); ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols); }
+  if constexpr (cta2) ptx::cluster_sync(); else __syncthreads();              // nobody signals a peer that has already left
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    if constexpr (cta2) ptx::tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -572,18 +625,58 @@ int pick_stages(int bn) {
 
 template <int OP>
 void launch(const CUtensorMap& a, const CUtensorMap& b, TcParams& p) {
-  p.stages = pick_stages(p.BN);
+  const int bn_local = p.cta2 ? p.BN / 2 : p.BN;
+  p.stages = pick_stages(bn_local);
   p.tmem_cols = tmem_cols_for(p.BN);
-  const size_t smem = smem_bytes_for(p.BN, p.stages);
+  const size_t smem = smem_bytes_for(bn_local, p.stages);
   static bool attr_set = false;
   if (!attr_set) {
-    CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<OP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<OP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<OP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  const int grid = std::min(p.num_tiles, num_sms());
-  tc_conv_kernel<OP><<<grid, kThreads, smem, state().stream>>>(a, b, p);
+  if (p.cta2) {
+    // one cluster of two CTAs (one TPC) per scheduling unit; persistent over the pair tiles
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2u * (unsigned)std::min(p.num_tiles, num_sms() / 2));
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = state().stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    CNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_conv_kernel<OP, true>, a, b, p));
+  } else {
+    const int grid = std::min(p.num_tiles, num_sms());
+    tc_conv_kernel<OP, false><<<grid, kThreads, smem, state().stream>>>(a, b, p);
+  }
   count_launch();
   CNB_LAUNCH_CHECK("tc_conv");
+}
+
+// CTA-pair mode (see TcParams::cta2). Worth it when the grid is full anyway: the pair halves the B bytes each SM
+// stages per k-block, and these kernels are bound by shared-memory fill rate, not by the tensor pipe.
+// `half_granule`: what BN/2 must be a multiple of (32-column atoms for MN-major B, 8 rows for K-major B).
+bool pair_enabled() {
+  static int en = -1;
+  if (en < 0) { const char* e = getenv("CONVNET_B200_NO_2CTA"); en = (e && e[0] == '1') ? 0 : 1; }
+  return en == 1;
+}
+void apply_pair(TcParams& p, int op, int half_granule, long long outer) {
+  p.cta2 = 0; p.m_groups = p.m_tiles;
+  // measured (profiles/): fprop gains 2-6 %, wgrad up to 48 % (conv2) when the o-tiles pair up evenly, dgrad loses
+  static const int ops = getenv("CONVNET_B200_2CTA_OPS") ? atoi(getenv("CONVNET_B200_2CTA_OPS")) : 5;
+  if (!pair_enabled() || !((ops >> op) & 1) || p.x_mode || p.m_tiles < 2) return;
+  if (op == kWgrad && (p.m_tiles & 1)) return;                     // an odd o-tile count would idle one CTA of the last pair
+  if (p.BN % (2 * half_granule) != 0 || p.BN < 2 * half_granule) return;
+  const long long pair_tiles = outer * ceil_div(p.m_tiles, 2) * p.n_tiles * p.splits;
+  if (pair_tiles < num_sms() / 2) return;                          // small problems keep every SM on its own tile
+  p.cta2 = 1;
+  p.m_groups = ceil_div(p.m_tiles, 2);
+  p.num_tiles = (int)pair_tiles;
+  p.b_tx_bytes = (uint32_t)(p.BN / 2) * BK * 4;
+  p.idesc = (p.idesc & ~(0x1Fu << 24)) | ((uint32_t)(2 * BM >> 4) << 24);   // M = 256
 }
 
 bool tc_enabled() {
@@ -601,6 +694,9 @@ void fill_common(TcParams& p, const ConvGeom& g) {
   p.splits = 1; p.units_per_split = 0;
   p.x_mode = 0; p.x_yblocks = 0; p.x_ct = 0; p.b_tx_bytes = 0;
   p.a_merged = 0; p.b_merged = 0;
+  p.cta2 = 0; p.m_groups = 0;
+  static const int dbg = getenv("CONVNET_B200_TC_DEBUG") ? atoi(getenv("CONVNET_B200_TC_DEBUG")) : 0;
+  p.dbg = dbg;
   p.bias = nullptr; p.relu = 0; p.mask = nullptr;
   p.out_frame_step = g.out_frame_step;
 }
@@ -661,6 +757,8 @@ bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, fl
   p.st = st; p.so = so;
   p.bias = fuse.bias ? fuse.bias + g.cout0 : nullptr; p.relu = fuse.relu;
   p.idesc = ptx::make_idesc(2, true, true, BM, p.BN);
+  apply_pair(p, kFprop, 32, 1);
+  const int bn_local = p.cta2 ? p.BN / 2 : p.BN;
   CUtensorMap ma, mb;
   const float* img = images + (long long)g.cin0 * g.H * g.W * g.N;
   static const bool allow_merge = !(getenv("CONVNET_B200_NO_TMA_MERGE") && getenv("CONVNET_B200_NO_TMA_MERGE")[0] == '1');
@@ -696,7 +794,7 @@ bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, fl
     if (p.b_merged) {
       const long long dims[4] = {32, g.Cin, g.Cout / 32, taps};
       const long long str[3] = {(long long)g.Cout * taps, 32, g.Cout};
-      const int box[4] = {32, BK, p.BN / 32, 1};
+      const int box[4] = {32, BK, bn_local / 32, 1};
       if (!make_map(&mb, filters, 4, dims, str, box, true)) return false;
     } else {
       const long long dims[3] = {g.Cout, taps, g.Cin};
@@ -727,6 +825,8 @@ bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, 
   p.so = so;
   p.b_tx_bytes = (uint32_t)p.BN * BK * 4;
   p.idesc = ptx::make_idesc(2, true, false, BM, p.BN);
+  apply_pair(p, kDgrad, 8, 1);
+  const int bn_local = p.cta2 ? p.BN / 2 : p.BN;
   CUtensorMap ma, mb;
   const float* der = derivs + (long long)g.cout0 * g.modules * g.N;
   static const bool allow_merge = !(getenv("CONVNET_B200_NO_TMA_MERGE") && getenv("CONVNET_B200_NO_TMA_MERGE")[0] == '1');
@@ -737,7 +837,7 @@ bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, 
   {
     const long long dims[3] = {g.Cout, (long long)g.kx * g.ky, g.Cin};
     const long long str[2] = {g.Cout, (long long)g.Cout * g.kx * g.ky};
-    const int box[3] = {32, 1, p.BN};
+    const int box[3] = {32, 1, bn_local};
     if (!make_map(&mb, filters, 3, dims, str, box, false)) return false;
   }
   float* out = targets + (long long)g.cin0 * g.H * g.W * g.N;
@@ -790,6 +890,8 @@ bool tc_conv_outp(const ConvGeom& g, const float* images, const float* derivs, f
   p.num_tiles = (int)(base_tiles * p.splits);
   p.st = st; p.so = so;
   p.idesc = ptx::make_idesc(2, false, false, BM, p.BN);
+  apply_pair(p, kWgrad, 8, x_mode ? 1 : p.taps);
+  const int bn_local = p.cta2 ? p.BN / 2 : p.BN;
   CUtensorMap ma, mb;
   const float* img = images + (long long)g.cin0 * g.H * g.W * g.N;
   const float* der = derivs + (long long)g.cout0 * g.modules * g.N;
@@ -800,7 +902,7 @@ bool tc_conv_outp(const ConvGeom& g, const float* images, const float* derivs, f
     const long long str[4] = {N, N * g.W, N * g.W * g.H, g.in_frame_step};
     const int box[5] = {32, 8, g.ky, 1, 1};                   // 8 x-taps x ky rows of one channel: ky*8 GEMM columns
     if (!make_map(&mb, img, 5, dims, str, box, false)) return false;
-  } else if (!image_map(&mb, img, g, g.W, g.H, g.Cin, g.in_frame_step, false, p.BN)) return false;
+  } else if (!image_map(&mb, img, g, g.W, g.H, g.Cin, g.in_frame_step, false, bn_local)) return false;
   if (p.splits == 1) {
     p.out = targets;
     launch<kWgrad>(ma, mb, p);
