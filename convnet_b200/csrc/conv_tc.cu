@@ -18,6 +18,7 @@
 // owns one image / one output channel row, so every store instruction writes 128 contiguous bytes).
 // Two TMEM accumulator buffers let the epilogue of tile i overlap the main loop of tile i+1.
 #include <cuda.h>
+#include <cuda_bf16.h>
 #include <cudaTypedefs.h>
 
 #include <algorithm>
@@ -31,13 +32,17 @@ namespace {
 
 constexpr int kThreads = 192;
 constexpr int BM = 128;             // GEMM rows per tile  (4 chunks of 32)
-constexpr int BK = 32;              // fp32 elements of K per pipeline stage (4 UMMA steps of 8)
+constexpr int BK = 32;              // fp32 (tf32) elements of K per pipeline stage (4 UMMA steps of 8); x-mode constant
 constexpr int kMaxStages = 8;
-constexpr uint32_t kAStageBytes = BM * BK * 4;   // 16 KiB
+constexpr uint32_t kAStageBytes = BM * 128;      // 16 KiB: 128 rows x 128 B (K-major) or chunks x bk rows x 128 B (MN-major)
 
 enum Op { kFprop = 0, kDgrad = 1, kWgrad = 2 };
 
 struct TcParams {
+  // operand element type: tf32 = the caller's fp32 buffers as they are; bf16 = bf16 copies made by a conversion pass.
+  // A 128-byte smem row holds `chunk` = 32 (tf32) or 64 (bf16) consecutive images / channels; one pipeline stage
+  // covers bk = 32 / 64 elements of K (four UMMA steps of 8 / 16) and an m-tile is cpt = 4 / 2 chunks of images.
+  int bf16, chunk, chunk_shift, cpt, bk, nbc;   // nbc = ceil(N / chunk)
   int N, nb;                        // images, ceil(N/32)
   int W, H, modX, modY, modules;
   int Cin, Cout;                    // channel sub-range sizes
@@ -57,9 +62,10 @@ struct TcParams {
   // CTA pairs (tcgen05 cta_group::2): two CTAs of a cluster share one 256 x BN tile; each loads its own 128 rows of A
   // and HALF of B, the leader issues M = 256 MMAs that read both shared memories, each CTA keeps its 128 rows in TMEM.
   int cta2;
-  int dbg;                          // CONVNET_B200_TC_DEBUG bits (timing experiments only): 1 = no TMA loads, 2 = no MMAs
+  int dbg;                          // CONVNET_B200_TC_DEBUG bits (timing experiments only): 1 = no TMA loads, 2 = no MMAs, 4 = no bf16 conversion
   int m_groups;                     // m-tiles (or o-tiles) per scheduling unit: m_tiles, or ceil(m_tiles/2) with cta2
-  int total_chunks;                 // fprop: nb*modules*frames ; dgrad: nb*W*H   (< 2^31, checked on the host)
+  int total_chunks;                 // fprop: nbc*modules*frames ; dgrad: nbc*W*H   (< 2^31, checked on the host)
+  int total_rows32;                 // the same count in 32-row units (what one epilogue warp owns)
   int splits, units_per_split;      // wgrad: (frame, module-row) units per reduction split
   float* out;
   float st, so;
@@ -114,10 +120,10 @@ __device__ __forceinline__ Chunks decode_chunks(const TcParams& p, int m_tile, i
   Chunks c;
 #pragma unroll
   for (int i = 0; i < 4; i++) {
-    const int q = m_tile * 4 + i;
-    c.ok[i] = q < p.total_chunks;
-    const int ib = q % p.nb, r = q / p.nb;
-    c.n[i] = c.ok[i] ? ib * 32 : p.N;        // n >= N: the whole TMA box is out of range -> zero-filled
+    const int q = m_tile * p.cpt + i;
+    c.ok[i] = i < p.cpt && q < p.total_chunks;
+    const int ib = q % p.nbc, r = q / p.nbc;
+    c.n[i] = c.ok[i] ? ib * p.chunk : p.N;   // n >= N: the whole TMA box is out of range -> zero-filled
     c.pos[i] = r % per_frame;
     c.f[i] = c.ok[i] ? r / per_frame : 0;
   }
@@ -191,12 +197,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr bool cta2 = PAIR;
   const int rank = cta2 ? (int)ptx::cluster_ctarank() : 0;          // 0 = leader of the pair
   const int bn_local = cta2 ? p.BN / 2 : p.BN;                      // B columns / rows this CTA stages
-  const uint32_t b_stage_bytes = (uint32_t)bn_local * BK * 4;
+  const uint32_t b_stage_bytes = (uint32_t)bn_local * 128;
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + (size_t)p.stages * kAStageBytes;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smemB + (size_t)p.stages * b_stage_bytes);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: provably warp-uniform, which keeps the role branches and their loops on the uniform path
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; s++) { ptx::mbar_init(&ctl->full[s], 1); ptx::mbar_init(&ctl->empty[s], 1); }
@@ -218,7 +225,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    {
+      const bool elected = ptx::elect_one();             // every lane walks the loops, one lane talks to the TMA unit
       int stage = 0; uint32_t phase = 0;
       const bool no_tma = (p.dbg & 1) != 0;
       const uint32_t tx_bytes = no_tma ? 0u : (kAStageBytes + p.b_tx_bytes) * (cta2 ? 2u : 1u);   // the leader's barrier counts both CTAs
@@ -226,22 +234,22 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const Tile tile = decode_tile<OP>(p, t, rank);
         auto begin_stage = [&]() -> uint8_t* {
           ptx::mbar_wait(&ctl->empty[stage], phase ^ 1);
-          if (rank == 0) ptx::mbar_arrive_expect_tx(&ctl->full[stage], tx_bytes);
+          if (rank == 0 && elected) ptx::mbar_arrive_expect_tx(&ctl->full[stage], tx_bytes);
           return smemA + (size_t)stage * kAStageBytes;
         };
         // TMA wrappers: in pair mode the completion bytes go to the leader's barrier
         auto lda5 = [&](const void* m, void* dst, int c0, int c1, int c2, int c3, int c4) {
-          if (no_tma) return;
+          if (no_tma || !elected) return;
           if constexpr (cta2) ptx::tma_load_5d_2sm(m, &ctl->full[stage], dst, c0, c1, c2, c3, c4);
           else ptx::tma_load_5d(m, &ctl->full[stage], dst, c0, c1, c2, c3, c4);
         };
         auto lda4 = [&](const void* m, void* dst, int c0, int c1, int c2, int c3) {
-          if (no_tma) return;
+          if (no_tma || !elected) return;
           if constexpr (cta2) ptx::tma_load_4d_2sm(m, &ctl->full[stage], dst, c0, c1, c2, c3);
           else ptx::tma_load_4d(m, &ctl->full[stage], dst, c0, c1, c2, c3);
         };
         auto lda3 = [&](const void* m, void* dst, int c0, int c1, int c2) {
-          if (no_tma) return;
+          if (no_tma || !elected) return;
           if constexpr (cta2) ptx::tma_load_3d_2sm(m, &ctl->full[stage], dst, c0, c1, c2);
           else ptx::tma_load_3d(m, &ctl->full[stage], dst, c0, c1, c2);
         };
@@ -260,6 +268,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               for (int yb = 0; yb < p.x_yblocks; yb++) {
                 uint8_t* a = begin_stage();
                 uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
+                if (!elected) { end_stage(); continue; }
                 if (p.a_merged) {                // dims (n_lo, x, y, n_hi, c): one 16 KiB request
                   ptx::tma_load_5d(&mapA, &ctl->full[stage], a, 0, cX[0], cY[0] + 4 * yb, ch.n[0] >> 5, c);
                 } else {
@@ -283,18 +292,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 uint8_t* a = begin_stage();
                 uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
                 if (p.a_merged) {                // dims (n_lo, c, n_hi, x, y): one 16 KiB request
-                  lda5(&mapA, a, 0, cb * BK, ch.n[0] >> 5, cX[0] + tx, cY[0] + ty);
+                  lda5(&mapA, a, 0, cb * p.bk, ch.n[0] >> p.chunk_shift, cX[0] + tx, cY[0] + ty);
                 } else {
 #pragma unroll
                   for (int c = 0; c < 4; c++)
-                    lda5(&mapA, a + c * (BK * 128), ch.n[c], cb * BK, cX[c] + tx, cY[c] + ty, ch.f[c]);
+                    if (c < p.cpt) lda5(&mapA, a + c * (p.bk * 128), ch.n[c], cb * p.bk, cX[c] + tx, cY[c] + ty, ch.f[c]);
                 }
                 const int o0 = tile.n_tile * p.BN + rank * bn_local;      // this CTA's share of the filter columns
                 if (p.b_merged) {                // dims (o_lo, c, o_hi, tap)
-                  lda4(&mapB, b, 0, cb * BK, o0 >> 5, tap);
+                  lda4(&mapB, b, 0, cb * p.bk, o0 >> p.chunk_shift, tap);
                 } else {
-                  for (int j = 0; j < bn_local / 32; j++)
-                    lda3(&mapB, b + j * (BK * 128), o0 + j * 32, tap, cb * BK);
+                  for (int j = 0; j < (bn_local >> p.chunk_shift); j++)
+                    lda3(&mapB, b + j * (p.bk * 128), o0 + j * p.chunk, tap, cb * p.bk);
                 }
                 end_stage();
               }
@@ -323,13 +332,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 uint8_t* a = begin_stage();
                 uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
                 if (p.a_merged) {                // all four chunks sit on the same pixel: dims (n_lo, o, n_hi, mx, my)
-                  lda5(&mapA, a, 0, ob * BK, ch.n[0] >> 5, mx[0], my[0]);
+                  lda5(&mapA, a, 0, ob * p.bk, ch.n[0] >> p.chunk_shift, mx[0], my[0]);
                 } else {
 #pragma unroll
                   for (int c = 0; c < 4; c++)
-                    lda5(&mapA, a + c * (BK * 128), ch.n[c], ob * BK, mx[c], my[c], p.frame0);
+                    if (c < p.cpt) lda5(&mapA, a + c * (p.bk * 128), ch.n[c], ob * p.bk, mx[c], my[c], p.frame0);
                 }
-                lda3(&mapB, b, ob * BK, tap, tile.n_tile * p.BN + rank * bn_local);
+                lda3(&mapB, b, ob * p.bk, tap, tile.n_tile * p.BN + rank * bn_local);
                 end_stage();
               }
             }
@@ -343,6 +352,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               for (int ib = 0; ib < p.nb; ib++) {
                 uint8_t* a = begin_stage();
                 uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
+                if (!elected) { end_stage(); continue; }
                 ptx::tma_load_5d(&mapA, &ctl->full[stage], a, ib * 32, mx, my, tile.o_tile * BM, f);
                 for (int c = 0; c < p.x_ct; c++)
                   ptx::tma_load_5d(&mapB, &ctl->full[stage], b + c * c_bytes, ib * 32, mx * p.sx + p.px, my * p.sy + p.py,
@@ -354,11 +364,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           const WgradSpan sp = wgrad_span(p, tile);
           const int tx = tile.tap % p.kx, ty = tile.tap / p.kx;
           if (sp.live_rows == 0) {                         // nothing to sum: one zero k-block group
-            for (int ib = 0; ib < p.nb; ib++) {
+            for (int ib = 0; ib < p.nbc; ib++) {
               uint8_t* a = begin_stage();
               uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
-              lda5(&mapA, a, ib * 32, 0, 0, tile.o_tile * BM, 0);
-              lda5(&mapB, b, ib * 32, -1, -1, tile.c_tile * p.BN + rank * bn_local, 0);
+              lda5(&mapA, a, ib * p.chunk, 0, 0, tile.o_tile * BM, 0);
+              lda5(&mapB, b, ib * p.chunk, -1, -1, tile.c_tile * p.BN + rank * bn_local, 0);
               end_stage();
             }
           } else {
@@ -368,11 +378,11 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               const int Y = my * p.sy + p.py + ty;
               for (int mx = sp.mx_lo; mx <= sp.mx_hi; mx++) {
                 const int X = mx * p.sx + p.px + tx;
-                for (int ib = 0; ib < p.nb; ib++) {
+                for (int ib = 0; ib < p.nbc; ib++) {
                   uint8_t* a = begin_stage();
                   uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
-                  lda5(&mapA, a, ib * 32, mx, my, tile.o_tile * BM, f);
-                  lda5(&mapB, b, ib * 32, X, Y, tile.c_tile * p.BN + rank * bn_local, f);
+                  lda5(&mapA, a, ib * p.chunk, mx, my, tile.o_tile * BM, f);
+                  lda5(&mapB, b, ib * p.chunk, X, Y, tile.c_tile * p.BN + rank * bn_local, f);
                   end_stage();
                 }
               }
@@ -390,11 +400,18 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     //    SBO = 512 B between 4-row groups, LBO = chunk stride, one UMMA (K = 8) = two groups = 1 KiB;
     //  K-major tiles are [row][128 B] in SWIZZLE_128B: SBO = 8 rows = 1 KiB, K step = 32 B inside the atom.
     const bool a_mn = (OP != kWgrad), b_mn = (OP == kFprop);
-    const uint32_t a_lbo = a_mn ? BK * 128 : 16, b_lbo = b_mn ? BK * 128 : 16;
-    const uint32_t a_sbo = a_mn ? 512 : 1024, b_sbo = b_mn ? 512 : 1024;
-    const uint32_t a_lay = a_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
-    const uint32_t b_lay = b_mn ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
-    const uint32_t a_kstep = a_mn ? 1024 : 32, b_kstep = b_mn ? 1024 : 32;
+    //  MN-major bf16 tiles are [chunk][bk rows][128 B] in plain SWIZZLE_128B: atoms of 8 K-rows x 128 B (64 elements of
+    //    M/N), SBO = 1 KiB between 8-row groups, LBO = chunk stride, one UMMA (K = 16) = two groups = 2 KiB.
+    const uint32_t mn_lbo = (uint32_t)p.bk * 128, mn_sbo = p.bf16 ? 1024 : 512, mn_kstep = p.bf16 ? 2048 : 1024;
+    const uint32_t mn_lay = p.bf16 ? ptx::kLayoutSw128 : ptx::kLayoutSw128Base32;
+    const uint32_t a_lbo = a_mn ? mn_lbo : 16, b_lbo = b_mn ? mn_lbo : 16;
+    const uint32_t a_sbo = a_mn ? mn_sbo : 1024, b_sbo = b_mn ? mn_sbo : 1024;
+    const uint32_t a_lay = a_mn ? mn_lay : ptx::kLayoutSw128;
+    const uint32_t b_lay = b_mn ? mn_lay : ptx::kLayoutSw128;
+    const uint32_t a_kstep = a_mn ? mn_kstep : 32, b_kstep = b_mn ? mn_kstep : 32;
+    const uint64_t da_base = ptx::make_smem_desc(ptx::smem_u32(smemA), a_lbo, a_sbo, a_lay);
+    const uint64_t db_base = ptx::make_smem_desc(ptx::smem_u32(smemB), b_lbo, b_sbo, b_lay);
+    const bool elected = ptx::elect_one();               // the warp stays converged; one lane issues
     for (int t = t_first; t < p.num_tiles; t += t_step) {
       const Tile tile = decode_tile<OP>(p, t, rank);
       int nkb;
@@ -409,7 +426,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         nkb = (r1 - r0) * p.modX * p.nb;
       } else {
         const WgradSpan sp = wgrad_span(p, tile);
-        nkb = max(sp.live_rows * (sp.mx_hi - sp.mx_lo + 1), 1) * p.nb;
+        nkb = max(sp.live_rows * (sp.mx_hi - sp.mx_lo + 1), 1) * p.nbc;
       }
       ptx::mbar_wait(&ctl->tmem_empty[acc], acc_phase ^ 1);
       ptx::tc_fence_after();
@@ -417,17 +434,23 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       for (int kb = 0; kb < nkb; kb++) {
         ptx::mbar_wait(&ctl->full[stage], phase);
         ptx::tc_fence_after();
-        if (lane == 0) {
+        if (elected) {
           if (!(p.dbg & 2)) {
-          const uint32_t a_addr = ptx::smem_u32(smemA + (size_t)stage * kAStageBytes);
-          const uint32_t b_addr = ptx::smem_u32(smemB + (size_t)stage * b_stage_bytes);
+            // descriptors differ from the stage-0 / step-0 ones only in the 14-bit start-address field (16-byte units)
+            const uint64_t da0 = da_base + (uint32_t)(stage * (int)(kAStageBytes >> 4));
+            const uint64_t db0 = db_base + (uint32_t)(stage * (int)(b_stage_bytes >> 4));
 #pragma unroll
-          for (int ks = 0; ks < BK / 8; ks++) {
-            const uint64_t da = ptx::make_smem_desc(a_addr + ks * a_kstep, a_lbo, a_sbo, a_lay);
-            const uint64_t db = ptx::make_smem_desc(b_addr + ks * b_kstep, b_lbo, b_sbo, b_lay);
-            if constexpr (cta2) ptx::mma_tf32_2sm(d_tmem, da, db, p.idesc, (kb | ks) != 0);
-            else ptx::mma_tf32(d_tmem, da, db, p.idesc, (kb | ks) != 0);
-          }
+            for (int ks = 0; ks < 4; ks++) {               // 4 UMMA steps per stage for both element types
+              const uint64_t da = da0 + (uint32_t)(ks * (int)(a_kstep >> 4)), db = db0 + (uint32_t)(ks * (int)(b_kstep >> 4));
+              const uint32_t accum = (kb | ks) != 0;
+              if (p.bf16) {
+                if constexpr (cta2) ptx::mma_bf16_2sm(d_tmem, da, db, p.idesc, accum);
+                else ptx::mma_bf16(d_tmem, da, db, p.idesc, accum);
+              } else {
+                if constexpr (cta2) ptx::mma_tf32_2sm(d_tmem, da, db, p.idesc, accum);
+                else ptx::mma_tf32(d_tmem, da, db, p.idesc, accum);
+              }
+            }
           }
           if constexpr (cta2) {                                       // frees the slot / publishes the accumulator in BOTH CTAs
             ptx::mma_commit_2sm(&ctl->empty[stage], 3);
@@ -456,7 +479,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (OP == kFprop || OP == kDgrad) {
         const int q = tile.m_tile * 4 + quarter;
         const int per_frame = (OP == kFprop) ? p.modules : p.W * p.H;
-        if (q < p.total_chunks) {
+        if (q < p.total_rows32) {
           const int ib = q % p.nb, r = q / p.nb, pos = r % per_frame, f = r / per_frame;
           const int n = ib * 32 + lane;
           if (n < p.N) {
@@ -576,8 +599,12 @@ PFN_cuTensorMapEncodeTiled_v12000 encode_fn() {
   return fn;
 }
 
-// fp32 tensor map; dims[0] is the contiguous axis; strides in ELEMENTS for dims 1..rank-1
-bool make_map(CUtensorMap* map, const float* base, int rank, const long long* dims, const long long* strides,
+// operand element type of one launch (see TcParams)
+struct Elem { int bf16, esz, chunk, shift, bk; };
+inline Elem elem_for(bool bf16) { return bf16 ? Elem{1, 2, 64, 6, 64} : Elem{0, 4, 32, 5, 32}; }
+
+// tensor map over fp32 or bf16 data; dims[0] is the contiguous axis; strides in ELEMENTS for dims 1..rank-1
+bool make_map(CUtensorMap* map, const void* base, const Elem& e, int rank, const long long* dims, const long long* strides,
               const int* box, bool mn_major) {
   cuuint64_t gdim[5], gstr[4];
   cuuint32_t bdim[5], estr[5];
@@ -589,14 +616,15 @@ bool make_map(CUtensorMap* map, const float* base, int rank, const long long* di
     estr[i] = 1;
     if (box[i] > 256) return false;
     if (i > 0) {
-      const long long bytes = strides[i - 1] * 4;
+      const long long bytes = strides[i - 1] * e.esz;
       if (bytes % 16 != 0 || bytes <= 0 || bytes >= (1LL << 40)) return false;
       gstr[i - 1] = (cuuint64_t)bytes;
     }
   }
-  CUresult r = encode_fn()(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank, const_cast<float*>(base), gdim, gstr,
-                           bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                           mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+  // 32-bit MN-major operands need the 32-byte-atom flavour of the 128-byte swizzle (UMMA SWIZZLE_128B_BASE32B)
+  const CUtensorMapSwizzle sw = (mn_major && !e.bf16) ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  CUresult r = encode_fn()(map, e.bf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, (cuuint32_t)rank,
+                           const_cast<void*>(base), gdim, gstr, bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, sw,
                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     fprintf(stderr, "convnet_b200: cuTensorMapEncodeTiled failed (%d)\n", (int)r);
@@ -614,7 +642,7 @@ int pick_bn(int cols, int granule) {              // N-tile: as wide as possible
 int tmem_cols_for(int bn) { int c = 32; while (c < 2 * bn) c *= 2; return c; }
 
 size_t smem_bytes_for(int bn, int stages) {
-  return 1024 + (size_t)stages * (kAStageBytes + (size_t)bn * BK * 4) + sizeof(SmemCtl) + 16;
+  return 1024 + (size_t)stages * (kAStageBytes + (size_t)bn * 128) + sizeof(SmemCtl) + 16;
 }
 
 int pick_stages(int bn) {
@@ -675,18 +703,23 @@ void apply_pair(TcParams& p, int op, int half_granule, long long outer) {
   p.cta2 = 1;
   p.m_groups = ceil_div(p.m_tiles, 2);
   p.num_tiles = (int)pair_tiles;
-  p.b_tx_bytes = (uint32_t)(p.BN / 2) * BK * 4;
+  p.b_tx_bytes = (uint32_t)(p.BN / 2) * 128;
   p.idesc = (p.idesc & ~(0x1Fu << 24)) | ((uint32_t)(2 * BM >> 4) << 24);   // M = 256
 }
 
 bool tc_enabled() {
   static int en = -1;
   if (en < 0) { const char* e = getenv("CONVNET_B200_DISABLE_TC"); en = (e && e[0] == '1') ? 0 : 1; }
-  return en == 1 && state().precision == kPrecTF32;
+  return en == 1 && state().precision >= kPrecTF32;
+}
+bool allow_merge() {
+  static const bool v = !(getenv("CONVNET_B200_NO_TMA_MERGE") && getenv("CONVNET_B200_NO_TMA_MERGE")[0] == '1');
+  return v;
 }
 
-void fill_common(TcParams& p, const ConvGeom& g) {
-  p.N = g.N; p.nb = ceil_div(g.N, 32);
+void fill_common(TcParams& p, const ConvGeom& g, const Elem& e) {
+  p.bf16 = e.bf16; p.chunk = e.chunk; p.chunk_shift = e.shift; p.cpt = BM / e.chunk; p.bk = e.bk;
+  p.N = g.N; p.nb = ceil_div(g.N, 32); p.nbc = ceil_div(g.N, e.chunk);
   p.W = g.W; p.H = g.H; p.modX = g.modX; p.modY = g.modY; p.modules = g.modules;
   p.Cin = g.Cin; p.Cout = g.Cout;
   p.kx = g.kx; p.ky = g.ky; p.sx = g.sx; p.sy = g.sy; p.px = g.px; p.py = g.py; p.taps = g.kx * g.ky;
@@ -699,146 +732,205 @@ void fill_common(TcParams& p, const ConvGeom& g) {
   p.dbg = dbg;
   p.bias = nullptr; p.relu = 0; p.mask = nullptr;
   p.out_frame_step = g.out_frame_step;
+  p.total_chunks = p.total_rows32 = 0;
 }
 
 // image-like tensor (N, W, H, C[, frames]) as a 5-D map ordered (n, c, x, y, f) or (n, x, y, c, f)
-bool image_map(CUtensorMap* m, const float* base, const ConvGeom& g, int Wd, int Hd, int C, long long frame_step,
-               bool channel_second, int box_c) {
+bool image_map(CUtensorMap* m, const void* base, const Elem& e, const ConvGeom& g, int Wd, int Hd, int C,
+               long long frame_step, bool channel_second, int box_c) {
   const long long N = g.N;
   if (channel_second) {
     const long long dims[5] = {N, C, Wd, Hd, g.frames};
     const long long str[4] = {N * Wd * Hd, N, N * Wd, frame_step};
-    const int box[5] = {32, box_c, 1, 1, 1};
-    return make_map(m, base, 5, dims, str, box, true);
+    const int box[5] = {e.chunk, box_c, 1, 1, 1};
+    return make_map(m, base, e, 5, dims, str, box, true);
   }
   const long long dims[5] = {N, Wd, Hd, C, g.frames};
   const long long str[4] = {N, N * Wd, N * Wd * Hd, frame_step};
-  const int box[5] = {32, 1, 1, box_c, 1};
-  return make_map(m, base, 5, dims, str, box, false);
+  const int box[5] = {e.chunk, 1, 1, box_c, 1};
+  return make_map(m, base, e, 5, dims, str, box, false);
 }
 
-// (n_lo = 32, channel / x / y ..., n_hi = N/32) view for one-request A tiles; `x_mode`: box {32, 8x, 4y, 4 n_hi, 1c}
-bool merged_image_map(CUtensorMap* m, const float* base, const ConvGeom& g, int Wd, int Hd, int C, bool x_mode) {
+// (n_lo = chunk, channel / x / y ..., n_hi = N/chunk) view for one-request A tiles; `x_mode`: box {32, 8x, 4y, 4 n_hi, 1c}
+bool merged_image_map(CUtensorMap* m, const void* base, const Elem& e, const ConvGeom& g, int Wd, int Hd, int C, bool x_mode) {
   const long long N = g.N;
   if (x_mode) {
     const long long dims[5] = {32, Wd, Hd, N / 32, C};
     const long long str[4] = {N, N * Wd, 32, N * Wd * Hd};
     const int box[5] = {32, 8, 4, 4, 1};
-    return make_map(m, base, 5, dims, str, box, true);
+    return make_map(m, base, e, 5, dims, str, box, true);
   }
-  const long long dims[5] = {32, C, N / 32, Wd, Hd};
-  const long long str[4] = {N * Wd * Hd, 32, N, N * Wd};
-  const int box[5] = {32, BK, 4, 1, 1};
-  return make_map(m, base, 5, dims, str, box, true);
+  const long long dims[5] = {e.chunk, C, N / e.chunk, Wd, Hd};
+  const long long str[4] = {N * Wd * Hd, e.chunk, N, N * Wd};
+  const int box[5] = {e.chunk, e.bk, BM / e.chunk, 1, 1};
+  return make_map(m, base, e, 5, dims, str, box, true);
 }
+
+// ---- bf16 staging: one HBM-bound pass fp32 -> bf16 (round to nearest even) per operand -------------
+__global__ void __launch_bounds__(256) cvt_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
+  const long long n8 = n >> 3;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
+    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
+    __nv_bfloat162 r0 = __floats2bfloat162_rn(a.x, a.y), r1 = __floats2bfloat162_rn(a.z, a.w);
+    __nv_bfloat162 r2 = __floats2bfloat162_rn(b.x, b.y), r3 = __floats2bfloat162_rn(b.z, b.w);
+    uint4 o;
+    o.x = *reinterpret_cast<uint32_t*>(&r0); o.y = *reinterpret_cast<uint32_t*>(&r1);
+    o.z = *reinterpret_cast<uint32_t*>(&r2); o.w = *reinterpret_cast<uint32_t*>(&r3);
+    reinterpret_cast<uint4*>(dst)[i] = o;
+  }
+  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) dst[(n8 << 3) + threadIdx.x] = __float2bfloat16_rn(src[(n8 << 3) + threadIdx.x]);
+}
+void to_bf16(const float* src, __nv_bfloat16* dst, long long n) {
+  static const int dbg = getenv("CONVNET_B200_TC_DEBUG") ? atoi(getenv("CONVNET_B200_TC_DEBUG")) : 0;
+  if (dbg & 4) return;
+  const long long n8 = n >> 3;
+  const int grid = (int)std::min<long long>(std::max<long long>(ceil_div<long long>(n8, 256), 1), 8LL * num_sms());
+  cvt_bf16_kernel<<<grid, 256, 0, state().stream>>>(src, dst, n);
+  count_launch();
+  CNB_LAUNCH_CHECK("cvt_bf16");
+}
+inline size_t align_up(size_t v) { return (v + 1023) & ~size_t(1023); }
+bool want_bf16() { return state().precision == kPrecBF16; }
+inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
 }  // namespace
 
 // ---- fprop ---------------------------------------------------------------------------------------
-bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, float* targets, float st, float so,
-                const Fuse& fuse) {
-  if (!tc_enabled() || !g.conv) return false;
+// `bf` selects bf16 operands (CONVNET_B200_PRECISION=bf16): images and filters are first rounded to bf16 copies in
+// library scratch, then the same kernel runs kind::f16 MMAs at twice the tf32 rate on half the operand bytes.
+static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float* filters, float* targets, float st, float so,
+                            const Fuse& fuse, bool bf) {
+  const Elem e = elem_for(bf);
   if (g.N % 4 != 0 || g.Cout % 4 != 0) return false;                        // TMA stride alignment
   const bool x_mode = g.Cin < 8;                                            // tiny channel counts: taps take the K block
   if (x_mode && (g.kx > 8 || g.ky > 8)) return false;
-  TcParams p; fill_common(p, g);
-  p.BN = pick_bn(g.Cout, 32);
-  p.kc_blocks = ceil_div(g.Cin, BK);
+  if (bf && (x_mode || g.N % 64 != 0 || g.Cout % 8 != 0 || !aligned16(images) || !aligned16(filters))) return false;
+  TcParams p; fill_common(p, g, e);
+  p.BN = pick_bn(g.Cout, e.chunk);
+  p.kc_blocks = ceil_div(g.Cin, e.bk);
   p.x_mode = x_mode ? 1 : 0;
   p.x_yblocks = ceil_div(g.ky, 4);
-  p.b_tx_bytes = (uint32_t)p.BN * BK * 4;
+  p.b_tx_bytes = (uint32_t)p.BN * 128;
   const long long chunks = (long long)p.nb * g.modules * g.frames;
   if (chunks * 4 >= (1LL << 31)) return false;
-  p.total_chunks = (int)chunks;
-  p.m_tiles = ceil_div(p.total_chunks, 4);
+  p.total_rows32 = (int)chunks;
+  p.total_chunks = p.nbc * g.modules * g.frames;
+  p.m_tiles = ceil_div(p.total_chunks, p.cpt);
   p.n_tiles = ceil_div(g.Cout, p.BN);
   p.num_tiles = p.m_tiles * p.n_tiles;
   p.out = targets + (long long)g.cout0 * g.modules * g.N;
   p.st = st; p.so = so;
   p.bias = fuse.bias ? fuse.bias + g.cout0 : nullptr; p.relu = fuse.relu;
-  p.idesc = ptx::make_idesc(2, true, true, BM, p.BN);
-  apply_pair(p, kFprop, 32, 1);
+  p.idesc = ptx::make_idesc(bf ? 1 : 2, true, true, BM, p.BN);
+  apply_pair(p, kFprop, e.chunk, 1);
   const int bn_local = p.cta2 ? p.BN / 2 : p.BN;
   CUtensorMap ma, mb;
-  const float* img = images + (long long)g.cin0 * g.H * g.W * g.N;
-  static const bool allow_merge = !(getenv("CONVNET_B200_NO_TMA_MERGE") && getenv("CONVNET_B200_NO_TMA_MERGE")[0] == '1');
-  p.a_merged = (allow_merge && g.frames == 1 && g.N % 128 == 0) ? 1 : 0;
-  p.b_merged = (allow_merge && g.Cout % 32 == 0) ? 1 : 0;
+  const long long img_off = (long long)g.cin0 * g.H * g.W * g.N;
+  const void* img = images + img_off;
+  const void* flt = filters;
   const long long taps = (long long)g.kx * g.ky;
+  if (bf) {
+    const size_t ib = align_up((size_t)g.img_total * 2), fb = align_up((size_t)g.Cout * g.K * 2);
+    uint8_t* ws = (uint8_t*)workspace(ib + fb);
+    to_bf16(images, (__nv_bfloat16*)ws, g.img_total);
+    to_bf16(filters, (__nv_bfloat16*)(ws + ib), (long long)g.Cout * g.K);
+    img = (const __nv_bfloat16*)ws + img_off;
+    flt = ws + ib;
+  }
+  p.a_merged = (allow_merge() && g.frames == 1 && g.N % 128 == 0) ? 1 : 0;
+  p.b_merged = (allow_merge() && g.Cout % e.chunk == 0) ? 1 : 0;
   // frames of a 3-D conv start in_frame_step floats apart and see Cin (= Cin3d*kt) channels
   if (x_mode) {
     const long long N = g.N;
     if (p.a_merged) {
-      if (!merged_image_map(&ma, img, g, g.W, g.H, g.Cin, true)) return false;
+      if (!merged_image_map(&ma, img, e, g, g.W, g.H, g.Cin, true)) return false;
     } else {
       const long long adims[5] = {N, g.Cin, g.W, g.H, g.frames};
       const long long astr[4] = {N * g.W * g.H, N, N * g.W, g.in_frame_step};
       const int abox[5] = {32, 1, 8, 4, 1};                     // 8 x-taps x 4 filter rows of one channel
-      if (!make_map(&ma, img, 5, adims, astr, abox, true)) return false;
+      if (!make_map(&ma, img, e, 5, adims, astr, abox, true)) return false;
     }
     if (p.b_merged) {
       const long long bdims[5] = {32, g.kx, g.ky, g.Cout / 32, g.Cin};
       const long long bstr[4] = {g.Cout, (long long)g.Cout * g.kx, 32, (long long)g.Cout * taps};
       const int bbox[5] = {32, 8, 4, p.BN / 32, 1};
-      if (!make_map(&mb, filters, 5, bdims, bstr, bbox, true)) return false;
+      if (!make_map(&mb, flt, e, 5, bdims, bstr, bbox, true)) return false;
     } else {
       const long long bdims[4] = {g.Cout, g.kx, g.ky, g.Cin};
       const long long bstr[3] = {g.Cout, (long long)g.Cout * g.kx, (long long)g.Cout * taps};
       const int bbox[4] = {32, 8, 4, 1};
-      if (!make_map(&mb, filters, 4, bdims, bstr, bbox, true)) return false;
+      if (!make_map(&mb, flt, e, 4, bdims, bstr, bbox, true)) return false;
     }
   } else {
     if (p.a_merged) {
-      if (!merged_image_map(&ma, img, g, g.W, g.H, g.Cin, false)) return false;
-    } else if (!image_map(&ma, img, g, g.W, g.H, g.Cin, g.in_frame_step, true, BK)) return false;
+      if (!merged_image_map(&ma, img, e, g, g.W, g.H, g.Cin, false)) return false;
+    } else if (!image_map(&ma, img, e, g, g.W, g.H, g.Cin, g.in_frame_step, true, e.bk)) return false;
     if (p.b_merged) {
-      const long long dims[4] = {32, g.Cin, g.Cout / 32, taps};
-      const long long str[3] = {(long long)g.Cout * taps, 32, g.Cout};
-      const int box[4] = {32, BK, bn_local / 32, 1};
-      if (!make_map(&mb, filters, 4, dims, str, box, true)) return false;
+      const long long dims[4] = {e.chunk, g.Cin, g.Cout / e.chunk, taps};
+      const long long str[3] = {(long long)g.Cout * taps, e.chunk, g.Cout};
+      const int box[4] = {e.chunk, e.bk, bn_local / e.chunk, 1};
+      if (!make_map(&mb, flt, e, 4, dims, str, box, true)) return false;
     } else {
       const long long dims[3] = {g.Cout, taps, g.Cin};
       const long long str[2] = {g.Cout, (long long)g.Cout * taps};
-      const int box[3] = {32, 1, BK};
-      if (!make_map(&mb, filters, 3, dims, str, box, true)) return false;
+      const int box[3] = {e.chunk, 1, e.bk};
+      if (!make_map(&mb, flt, e, 3, dims, str, box, true)) return false;
     }
   }
   launch<kFprop>(ma, mb, p);
-  state().last_conv_path = kPathTcTf32;
+  state().last_conv_path = bf ? kPathTcBf16 : kPathTcTf32;
   return true;
+}
+bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, float* targets, float st, float so,
+                const Fuse& fuse) {
+  if (!tc_enabled() || !g.conv) return false;
+  if (want_bf16() && tc_conv_up_impl(g, images, filters, targets, st, so, fuse, true)) return true;
+  return tc_conv_up_impl(g, images, filters, targets, st, so, fuse, false);
 }
 
 // ---- dgrad ---------------------------------------------------------------------------------------
-bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float st, float so,
-                  const Fuse& fuse) {
-  if (!tc_enabled() || !g.conv) return false;
+static bool tc_conv_down_impl(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float st, float so,
+                              const Fuse& fuse, bool bf) {
+  const Elem e = elem_for(bf);
   if (g.N % 4 != 0 || g.Cout % 4 != 0 || g.Cout < 8 || g.Cin < 8) return false;
-  TcParams p; fill_common(p, g);
+  if (bf && (g.N % 64 != 0 || g.Cout % 8 != 0 || !aligned16(derivs) || !aligned16(filters))) return false;
+  TcParams p; fill_common(p, g, e);
   p.BN = pick_bn(g.Cin, 16);
-  p.kc_blocks = ceil_div(g.Cout, BK);
+  p.kc_blocks = ceil_div(g.Cout, e.bk);
   const long long chunks = (long long)p.nb * g.W * g.H;
   if (chunks * 4 >= (1LL << 31) || g.kx > 32 || g.ky > 32) return false;
-  p.total_chunks = (int)chunks;
-  p.m_tiles = ceil_div(p.total_chunks, 4);
+  p.total_rows32 = (int)chunks;
+  p.total_chunks = p.nbc * g.W * g.H;
+  p.m_tiles = ceil_div(p.total_chunks, p.cpt);
   p.n_tiles = ceil_div(g.Cin, p.BN);
   p.num_tiles = p.m_tiles * p.n_tiles;
   p.so = so;
-  p.b_tx_bytes = (uint32_t)p.BN * BK * 4;
-  p.idesc = ptx::make_idesc(2, true, false, BM, p.BN);
+  p.b_tx_bytes = (uint32_t)p.BN * 128;
+  p.idesc = ptx::make_idesc(bf ? 1 : 2, true, false, BM, p.BN);
   apply_pair(p, kDgrad, 8, 1);
   const int bn_local = p.cta2 ? p.BN / 2 : p.BN;
   CUtensorMap ma, mb;
-  const float* der = derivs + (long long)g.cout0 * g.modules * g.N;
-  static const bool allow_merge = !(getenv("CONVNET_B200_NO_TMA_MERGE") && getenv("CONVNET_B200_NO_TMA_MERGE")[0] == '1');
-  p.a_merged = (allow_merge && g.frames == 1 && g.N % 128 == 0) ? 1 : 0;
+  const long long der_off = (long long)g.cout0 * g.modules * g.N;
+  const void* der = derivs + der_off;
+  const void* flt = filters;
+  if (bf) {
+    const size_t db = align_up((size_t)g.out_total * 2), fb = align_up((size_t)g.Cout * g.K * 2);
+    uint8_t* ws = (uint8_t*)workspace(db + fb);
+    to_bf16(derivs, (__nv_bfloat16*)ws, g.out_total);
+    to_bf16(filters, (__nv_bfloat16*)(ws + db), (long long)g.Cout * g.K);
+    der = (const __nv_bfloat16*)ws + der_off;
+    flt = ws + db;
+  }
+  p.a_merged = (allow_merge() && g.frames == 1 && g.N % 128 == 0) ? 1 : 0;
   if (p.a_merged) {
-    if (!merged_image_map(&ma, der, g, g.modX, g.modY, g.Cout, false)) return false;
-  } else if (!image_map(&ma, der, g, g.modX, g.modY, g.Cout, g.out_frame_step, true, BK)) return false;
+    if (!merged_image_map(&ma, der, e, g, g.modX, g.modY, g.Cout, false)) return false;
+  } else if (!image_map(&ma, der, e, g, g.modX, g.modY, g.Cout, g.out_frame_step, true, e.bk)) return false;
   {
     const long long dims[3] = {g.Cout, (long long)g.kx * g.ky, g.Cin};
     const long long str[2] = {g.Cout, (long long)g.Cout * g.kx * g.ky};
-    const int box[3] = {32, 1, bn_local};
-    if (!make_map(&mb, filters, 3, dims, str, box, false)) return false;
+    const int box[3] = {e.chunk, 1, bn_local};
+    if (!make_map(&mb, flt, e, 3, dims, str, box, false)) return false;
   }
   float* out = targets + (long long)g.cin0 * g.H * g.W * g.N;
   const bool whole = (g.frames == 1 && g.cin0 == 0 && g.Cin == g.CinT);
@@ -855,19 +947,26 @@ bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, 
       launch<kDgrad>(ma, mb, p);
     }
   }
-  state().last_conv_path = kPathTcTf32;
+  state().last_conv_path = bf ? kPathTcBf16 : kPathTcTf32;
   return true;
+}
+bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float st, float so,
+                  const Fuse& fuse) {
+  if (!tc_enabled() || !g.conv) return false;
+  if (want_bf16() && tc_conv_down_impl(g, derivs, filters, targets, st, so, fuse, true)) return true;
+  return tc_conv_down_impl(g, derivs, filters, targets, st, so, fuse, false);
 }
 
 // ---- wgrad ---------------------------------------------------------------------------------------
-bool tc_conv_outp(const ConvGeom& g, const float* images, const float* derivs, float* targets, float st, float so) {
-  if (!tc_enabled() || !g.conv) return false;
+static bool tc_conv_outp_impl(const ConvGeom& g, const float* images, const float* derivs, float* targets, float st, float so,
+                              bool bf) {
+  const Elem e = elem_for(bf);
   if (g.N % 4 != 0 || g.Cout < 8) return false;
   const bool x_mode = g.Cin < 8;
   if (x_mode && (g.kx > 8 || g.ky > 8)) return false;
-  TcParams p; fill_common(p, g);
+  if (bf && (x_mode || g.N % 64 != 0 || !aligned16(images) || !aligned16(derivs))) return false;
+  TcParams p; fill_common(p, g, e);
   p.kc_blocks = 0;
-  p.total_chunks = 0;
   p.m_tiles = ceil_div(g.Cout, BM);
   if (x_mode) {
     p.x_mode = 1;
@@ -878,7 +977,7 @@ bool tc_conv_outp(const ConvGeom& g, const float* images, const float* derivs, f
   } else {
     p.BN = pick_bn(g.Cin, 16);
     p.n_tiles = ceil_div(g.Cin, p.BN);
-    p.b_tx_bytes = (uint32_t)p.BN * BK * 4;
+    p.b_tx_bytes = (uint32_t)p.BN * 128;
   }
   const int units = g.modY * g.frames;               // reduction units = module rows
   const long long base_tiles = (long long)(x_mode ? 1 : p.taps) * p.m_tiles * p.n_tiles;
@@ -889,31 +988,49 @@ bool tc_conv_outp(const ConvGeom& g, const float* images, const float* derivs, f
   p.splits = ceil_div(units, p.units_per_split);
   p.num_tiles = (int)(base_tiles * p.splits);
   p.st = st; p.so = so;
-  p.idesc = ptx::make_idesc(2, false, false, BM, p.BN);
+  p.idesc = ptx::make_idesc(bf ? 1 : 2, false, false, BM, p.BN);
   apply_pair(p, kWgrad, 8, x_mode ? 1 : p.taps);
   const int bn_local = p.cta2 ? p.BN / 2 : p.BN;
   CUtensorMap ma, mb;
-  const float* img = images + (long long)g.cin0 * g.H * g.W * g.N;
-  const float* der = derivs + (long long)g.cout0 * g.modules * g.N;
-  if (!image_map(&ma, der, g, g.modX, g.modY, g.Cout, g.out_frame_step, false, BM)) return false;
+  const long long img_off = (long long)g.cin0 * g.H * g.W * g.N, der_off = (long long)g.cout0 * g.modules * g.N;
+  const void* img = images + img_off;
+  const void* der = derivs + der_off;
+  const size_t part_bytes = p.splits > 1 ? align_up(sizeof(float) * elems * p.splits) : 0;
+  uint8_t* ws = nullptr;
+  if (bf) {
+    const size_t ib = align_up((size_t)g.img_total * 2), db = align_up((size_t)g.out_total * 2);
+    ws = (uint8_t*)workspace(part_bytes + ib + db);
+    to_bf16(images, (__nv_bfloat16*)(ws + part_bytes), g.img_total);
+    to_bf16(derivs, (__nv_bfloat16*)(ws + part_bytes + ib), g.out_total);
+    img = (const __nv_bfloat16*)(ws + part_bytes) + img_off;
+    der = (const __nv_bfloat16*)(ws + part_bytes + ib) + der_off;
+  } else if (part_bytes) {
+    ws = (uint8_t*)workspace(part_bytes);
+  }
+  if (!image_map(&ma, der, e, g, g.modX, g.modY, g.Cout, g.out_frame_step, false, BM)) return false;
   if (x_mode) {
     const long long N = g.N;
     const long long dims[5] = {N, g.W, g.H, g.Cin, g.frames};
     const long long str[4] = {N, N * g.W, N * g.W * g.H, g.in_frame_step};
     const int box[5] = {32, 8, g.ky, 1, 1};                   // 8 x-taps x ky rows of one channel: ky*8 GEMM columns
-    if (!make_map(&mb, img, 5, dims, str, box, false)) return false;
-  } else if (!image_map(&mb, img, g, g.W, g.H, g.Cin, g.in_frame_step, false, bn_local)) return false;
+    if (!make_map(&mb, img, e, 5, dims, str, box, false)) return false;
+  } else if (!image_map(&mb, img, e, g, g.W, g.H, g.Cin, g.in_frame_step, false, bn_local)) return false;
   if (p.splits == 1) {
     p.out = targets;
     launch<kWgrad>(ma, mb, p);
   } else {
-    float* part = (float*)workspace(sizeof(float) * elems * p.splits);
+    float* part = (float*)ws;
     p.out = part;
     launch<kWgrad>(ma, mb, p);
     reduce_partials(part, targets, elems, 1, p.splits, st, so);
   }
-  state().last_conv_path = kPathTcTf32;
+  state().last_conv_path = bf ? kPathTcBf16 : kPathTcTf32;
   return true;
+}
+bool tc_conv_outp(const ConvGeom& g, const float* images, const float* derivs, float* targets, float st, float so) {
+  if (!tc_enabled() || !g.conv) return false;
+  if (want_bf16() && tc_conv_outp_impl(g, images, derivs, targets, st, so, true)) return true;
+  return tc_conv_outp_impl(g, images, derivs, targets, st, so, false);
 }
 
 }  // namespace cnb

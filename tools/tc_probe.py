@@ -40,6 +40,12 @@ def diff(a, b):
 
 def timed(fn, iters):
     fn(); torch.cuda.synchronize()
+    if iters > 1:                       # warm the clocks up: ~30 ms of the same kernel before the timed loop
+        t0 = time.time()
+        while time.time() - t0 < 0.03:
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(iters):
@@ -50,7 +56,7 @@ def timed(fn, iters):
 
 def main():
     names = sys.argv[1:] or list(SHAPES)
-    iters = int(os.environ.get("ITERS", "5"))
+    iters = int(os.environ.get("ITERS", "20"))
     for name in names:
         N, W, H, Cin, Cout, ky, kx, sy, sx, py, px = SHAPES[name]
         modY, modX = num_modules(H, ky, sy, py), num_modules(W, kx, sx, px)
@@ -62,20 +68,35 @@ def main():
         dv = CUDAMatrix(N, modX * modY * Cout, tsh); dv.storage.normal_(generator=g)
         flops = 2.0 * N * modX * modY * Cout * kx * ky * Cin
         res = {}
-        for mode in ("fp32", "tf32"):
+        fast = os.environ.get("MODE", "tf32")
+        ref_iters = 1 if os.environ.get("FAST_REF") else iters
+        for mode in ("fp32", fast):
             lib.set_precision(mode)
             up = CUDAMatrix(N, modX * modY * Cout, tsh); dn = CUDAMatrix(N, W * H * Cin, ish); dw = CUDAMatrix(Cout, kx * ky * Cin, fsh)
             up.fill_(float("nan")); dn.fill_(float("nan")); dw.fill_(float("nan"))
-            t_up = timed(lambda: cg.convUp(x, w, up, d), iters); p_up = lib.last_conv_path()
-            t_dn = timed(lambda: cg.convDown(dv, w, dn, d), iters); p_dn = lib.last_conv_path()
-            t_dw = timed(lambda: cg.convOutp(x, dv, dw, d, 0, 1.0 / N), iters); p_dw = lib.last_conv_path()
+            it = ref_iters if mode == "fp32" else iters
+            t_up = timed(lambda: cg.convUp(x, w, up, d), it); p_up = lib.last_conv_path()
+            t_dn = timed(lambda: cg.convDown(dv, w, dn, d), it); p_dn = lib.last_conv_path()
+            t_dw = timed(lambda: cg.convOutp(x, dv, dw, d, 0, 1.0 / N), it); p_dw = lib.last_conv_path()
             res[mode] = (up, dn, dw, (t_up, t_dn, t_dw), (p_up, p_dn, p_dw))
-        a, b = res["fp32"], res["tf32"]
+        a, b = res["fp32"], res[fast]
         for i, op in enumerate(("fprop", "dgrad", "wgrad")):
-            print("%-10s %-5s %-14s Diff=%.2e  fp32 %8.3f ms (%6.1f TF/s)   tf32 %8.3f ms (%7.1f TF/s)" % (
+            print("%-10s %-5s %-14s Diff=%.2e  fp32 %8.3f ms (%6.1f TF/s)   fast %8.3f ms (%7.1f TF/s)" % (
                 name, op, b[4][i], diff(a[i].storage, b[i].storage), a[3][i], flops / a[3][i] / 1e9,
                 b[3][i], flops / b[3][i] / 1e9), flush=True)
 
 
+def cublas_reference():
+    """cuBLAS through torch.matmul on the same box, same warm-up: the practical tensor ceiling next to our numbers."""
+    n = 8192
+    for dt, name in ((torch.bfloat16, "bf16"), (torch.float32, "tf32")):
+        torch.backends.cuda.matmul.allow_tf32 = True
+        a = torch.randn(n, n, device="cuda", dtype=dt); b = torch.randn(n, n, device="cuda", dtype=dt)
+        t = timed(lambda: torch.matmul(a, b), 10)
+        print("cublas %s %d^3: %.3f ms (%.1f TF/s)" % (name, n, t, 2.0 * n ** 3 / t / 1e9), flush=True)
+
+
 if __name__ == "__main__":
+    if os.environ.get("CUBLAS_REF"):
+        cublas_reference()
     main()
