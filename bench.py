@@ -47,12 +47,16 @@ class ClockSampler:
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, gpu_index):
-        self.rows, self.proc, self.idx = [], None, gpu_index
+        self.rows, self.proc, self.idx, self.windows = [], None, gpu_index, []
+
+    def window(self, t0, t1):
+        """a timed region [t0, t1] (time.time()): only samples taken inside a window are reported"""
+        self.windows.append((t0, t1))
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "25"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             threading.Thread(target=self._read, daemon=True).start()
         except Exception:
@@ -60,7 +64,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
+            self.rows.append((time.time(), [c.strip() for c in line.split(",")]))
 
     def stop(self):
         if self.proc:
@@ -69,10 +73,13 @@ class ClockSampler:
                 self.proc.wait(timeout=2)
             except Exception:
                 pass
-        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
-        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        # nvidia-smi prints a sample a few ms after taking it: accept rows up to 30 ms past a window's end
+        rows = [r for t, r in self.rows if any(a <= t <= b + 0.03 for a, b in self.windows)] if self.windows else \
+               [r for _, r in self.rows]
+        sm = [float(r[1]) for r in rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) < 9:
                 continue
             for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
@@ -139,18 +146,20 @@ def conv_roofline(torch, lib, peaks, peak_kind, iters=10):
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
             "traffic": None, "kernel": "tc_conv_kernel<fprop> (%s)" % path,
             "shape": "conv4 fprop 3x3 s1 p1, 14x14x768 -> 384, batch 256 (266.3 GFLOP)", "ms_per_launch": ms,
-            "peak_source": "%s bf16 burst peak (cuBLAS); the kernel multiplies in tf32, whose tensor peak is half of bf16" % peak_kind}
+            "peak_source": "%s bf16 burst peak (cuBLAS); %s" % (peak_kind, {
+                "tcgen05-bf16": "bf16 operands (fp32 -> bf16 staging pass inside the timed call), fp32 accumulate",
+                "tcgen05-tf32": "the kernel multiplies in tf32, whose tensor peak is half of bf16"}.get(path, path))}
 
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--model", default="alexnet")
     ap.add_argument("--batch", type=int, default=PER_GPU_BATCH, help="images per GPU")
-    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32"])
+    ap.add_argument("--precision", default="tf32", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--bucket-mb", type=float, default=32.0, help="gradient all-reduce bucket size")
     args = ap.parse_args()
@@ -221,18 +230,22 @@ def main():
         y_dev.copy_(y_host, non_blocking=True)
         losses.append(net.train_step(want_loss=True))        # D2H of the step's loss
 
-    for _ in range(args.warmup):
-        step_resident()
     sampler = ClockSampler(local_rank)
     if rank == 0:
-        sampler.start()
+        sampler.start()                                      # nvidia-smi needs ~1 s to deliver its first sample
+    for _ in range(args.warmup):
+        step_resident()
     L.convnet_b200_reset_launch_count()
+    t0 = time.time()
     ms_total = timed(step_resident, args.steps)
+    sampler.window(t0, time.time())
     launches = int(L.convnet_b200_launch_count())
-    clocks = sampler.stop() if rank == 0 else None
     for _ in range(2):
         step_e2e()
+    t0 = time.time()
     ms_e2e = timed(step_e2e, args.steps)
+    sampler.window(t0, time.time())                          # both timed regions run the same step under load
+    clocks = sampler.stop() if rank == 0 else None
 
     images = args.batch * world * args.steps
     value = images / (ms_total * 1e-3)
@@ -244,10 +257,11 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "tf32" if args.precision == "tf32" else "f32", "data": "synthetic",
+            "vs_baseline": None, "dtype": {"tf32": "tf32", "bf16": "bf16", "fp32": "f32"}[args.precision], "data": "synthetic",
             "config": {"workload": WORKLOAD if args.model == "alexnet" else args.model, "global_batch": args.batch * world,
                        "per_gpu_batch": args.batch, "parallelism": "dp%d" % world,
-                       "arithmetic": "fp32 storage; conv/1x1/fc multiply in tf32 on tcgen05 with fp32 accumulate; pool/rnorm/elementwise fp32",
+                       "arithmetic": "fp32 storage and master weights; conv/1x1/fc multiply in %s on tcgen05 with fp32 accumulate "
+                                     "(conv1, Cin=3, always tf32); pool/rnorm/elementwise fp32" % args.precision,
                        "l2": "no flush needed: one step streams >3 GB of activations/weights through the 126 MB L2",
                        "sync": "NCCL all-reduce(avg) of the flat gradient buffer in %.0f MB buckets overlapped with bprop" % args.bucket_mb
                                if world > 1 else "single GPU",

@@ -24,6 +24,11 @@ bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, 
 bool tc_conv_outp(const ConvGeom& g, const float* images, const float* derivs, float* targets,
                   float scaleTargets, float scaleOutput);
 
+// bf16 operand staging (convnet_b200_bf16_stage / _invalidate); release drops the buffers too
+void bf16_stage(const float* ptr, long long n);
+void bf16_invalidate(const float* ptr);
+void bf16_release();
+
 // pool.cu
 void pool_forward(const PoolGeom& g, bool is_max, const float* images, float* targets, float scaleOutput);
 void max_pool_undo(const PoolGeom& g, const float* images, const float* maxGrads, const float* maxActs,

@@ -22,6 +22,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <vector>
 
 #include "conv_kernels.h"
 #include "sm100_ptx.cuh"
@@ -65,8 +66,9 @@ struct TcParams {
   int dbg;                          // CONVNET_B200_TC_DEBUG bits (timing experiments only): 1 = no TMA loads, 2 = no MMAs, 4 = no bf16 conversion
   int m_groups;                     // m-tiles (or o-tiles) per scheduling unit: m_tiles, or ceil(m_tiles/2) with cta2
   int total_chunks;                 // fprop: nbc*modules*frames ; dgrad: nbc*W*H   (< 2^31, checked on the host)
-  int total_rows32;                 // the same count in 32-row units (what one epilogue warp owns)
-  int splits, units_per_split;      // wgrad: (frame, module-row) units per reduction split
+  int splits, units_per_split;      // wgrad: (frame, module-row) units per reduction split;
+                                    // fprop/dgrad of 1x1 / FC shapes with few tiles: K blocks per split (split-K)
+  long long part_stride;            // fprop/dgrad split-K: floats between the partial outputs of consecutive splits
   float* out;
   float st, so;
   const float* bias; int relu;      // fused fprop epilogue: + bias[o], then max(., 0)
@@ -103,10 +105,11 @@ __device__ __forceinline__ Tile decode_tile(const TcParams& p, int t, int rank) 
     r.tap = t;
     r.m_tile = r.o_tile; r.n_tile = r.c_tile;
   } else {
+    r.split = t % p.splits; t /= p.splits;
     r.n_tile = t % p.n_tiles;
     r.m_tile = t / p.n_tiles;
     if (p.cta2) r.m_tile = 2 * r.m_tile + rank;
-    r.tap = r.o_tile = r.c_tile = r.split = 0;
+    r.tap = r.o_tile = r.c_tile = 0;
   }
   return r;
 }
@@ -288,7 +291,10 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int ty = 0; ty < p.ky; ty++)
             for (int tx = 0; tx < p.kx; tx++) {
               const int tap = tx + p.kx * ty;
-              for (int cb = 0; cb < p.kc_blocks; cb++) {
+              // split-K (host: only when taps == 1): this tile reduces K blocks [cb0, cb1)
+              const int cb0 = p.splits > 1 ? tile.split * p.units_per_split : 0;
+              const int cb1 = p.splits > 1 ? min(cb0 + p.units_per_split, p.kc_blocks) : p.kc_blocks;
+              for (int cb = cb0; cb < cb1; cb++) {
                 uint8_t* a = begin_stage();
                 uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
                 if (p.a_merged) {                // dims (n_lo, c, n_hi, x, y): one 16 KiB request
@@ -328,7 +334,9 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 my[c] = lv ? (cY[c] - p.py - ty) / p.sy : -1;
               }
               const int tap = tx + p.kx * ty;
-              for (int ob = 0; ob < p.kc_blocks; ob++) {
+              const int ob0 = p.splits > 1 ? tile.split * p.units_per_split : 0;
+              const int ob1 = p.splits > 1 ? min(ob0 + p.units_per_split, p.kc_blocks) : p.kc_blocks;
+              for (int ob = ob0; ob < ob1; ob++) {
                 uint8_t* a = begin_stage();
                 uint8_t* b = smemB + (size_t)stage * b_stage_bytes;
                 if (p.a_merged) {                // all four chunks sit on the same pixel: dims (n_lo, o, n_hi, mx, my)
@@ -416,11 +424,13 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       const Tile tile = decode_tile<OP>(p, t, rank);
       int nkb;
       if (OP == kFprop) {
-        nkb = p.x_mode ? p.Cin * p.x_yblocks : p.taps * p.kc_blocks;
+        const int kcb = p.splits > 1 ? min(p.units_per_split, p.kc_blocks - tile.split * p.units_per_split) : p.kc_blocks;
+        nkb = p.x_mode ? p.Cin * p.x_yblocks : p.taps * kcb;
       } else if (OP == kDgrad) {
         const DgradTaps own = dgrad_taps(p, decode_chunks(p, tile.m_tile, p.W * p.H));
         const DgradTaps peer = cta2 ? dgrad_taps(p, decode_chunks(p, tile.m_tile ^ 1, p.W * p.H)) : own;
-        nkb = max(dgrad_live_taps(p, own, peer), 1) * p.kc_blocks;
+        const int kcb = p.splits > 1 ? min(p.units_per_split, p.kc_blocks - tile.split * p.units_per_split) : p.kc_blocks;
+        nkb = max(dgrad_live_taps(p, own, peer), 1) * kcb;
       } else if (p.x_mode) {
         const int r0 = tile.split * p.units_per_split, r1 = min(r0 + p.units_per_split, p.modY * p.frames);
         nkb = (r1 - r0) * p.modX * p.nb;
@@ -477,18 +487,21 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       int ncols_valid = 0;
       bool direct_scale = true;
       if (OP == kFprop || OP == kDgrad) {
-        const int q = tile.m_tile * 4 + quarter;
+        // this warp's 32 rows are one half (bf16: 64-image chunks) or the whole (tf32) of chunk qc of the tile
+        const int q = tile.m_tile * 4 + quarter, sub = p.chunk_shift - 5;
+        const int qc = q >> sub, half = q & ((1 << sub) - 1);
         const int per_frame = (OP == kFprop) ? p.modules : p.W * p.H;
-        if (q < p.total_rows32) {
-          const int ib = q % p.nb, r = q / p.nb, pos = r % per_frame, f = r / per_frame;
-          const int n = ib * 32 + lane;
+        if (qc < p.total_chunks) {
+          const int ib = qc % p.nbc, r = qc / p.nbc, pos = r % per_frame, f = r / per_frame;
+          const int n = ib * p.chunk + half * 32 + lane;
           if (n < p.N) {
             col_stride = (long long)p.N * per_frame;
             row_ptr = p.out + (OP == kFprop ? f * p.out_frame_step : 0) + n + (long long)p.N * pos +
-                      col_stride * ((long long)tile.n_tile * p.BN);
+                      col_stride * ((long long)tile.n_tile * p.BN) + tile.split * p.part_stride;
           }
         }
         ncols_valid = min(p.BN, (OP == kFprop ? p.Cout : p.Cin) - tile.n_tile * p.BN);
+        direct_scale = (p.splits == 1);
       } else if (p.x_mode) {
         // column j of the tile = tap tx + 8*(row ty + ky*channel): scattered to dW[o, tx + kx*(ty + ky*c)] below
         const int o = tile.o_tile * BM + quarter * 32 + lane;
@@ -724,7 +737,7 @@ void fill_common(TcParams& p, const ConvGeom& g, const Elem& e) {
   p.Cin = g.Cin; p.Cout = g.Cout;
   p.kx = g.kx; p.ky = g.ky; p.sx = g.sx; p.sy = g.sy; p.px = g.px; p.py = g.py; p.taps = g.kx * g.ky;
   p.frames = g.frames; p.frame0 = 0;
-  p.splits = 1; p.units_per_split = 0;
+  p.splits = 1; p.units_per_split = 0; p.part_stride = 0;
   p.x_mode = 0; p.x_yblocks = 0; p.x_ct = 0; p.b_tx_bytes = 0;
   p.a_merged = 0; p.b_merged = 0;
   p.cta2 = 0; p.m_groups = 0;
@@ -732,7 +745,7 @@ void fill_common(TcParams& p, const ConvGeom& g, const Elem& e) {
   p.dbg = dbg;
   p.bias = nullptr; p.relu = 0; p.mask = nullptr;
   p.out_frame_step = g.out_frame_step;
-  p.total_chunks = p.total_rows32 = 0;
+  p.total_chunks = 0;
 }
 
 // image-like tensor (N, W, H, C[, frames]) as a 5-D map ordered (n, c, x, y, f) or (n, x, y, c, f)
@@ -791,10 +804,101 @@ void to_bf16(const float* src, __nv_bfloat16* dst, long long n) {
   CNB_LAUNCH_CHECK("cvt_bf16");
 }
 inline size_t align_up(size_t v) { return (v + 1023) & ~size_t(1023); }
+
+// staged bf16 copies (convnet_b200_bf16_stage): a small table keyed by the fp32 tensor's base pointer
+struct Staged { const float* src; long long n; __nv_bfloat16* buf; size_t cap; bool valid; unsigned long long tick; };
+std::vector<Staged>& staged_table() { static std::vector<Staged> t; return t; }
+unsigned long long g_stage_tick = 0;
+constexpr size_t kMaxStaged = 96;
+const __nv_bfloat16* staged(const float* src, long long n) {          // nullptr: not staged (or too short)
+  for (Staged& e : staged_table())
+    if (e.valid && e.src == src && e.n >= n) { e.tick = ++g_stage_tick; return e.buf; }
+  return nullptr;
+}
+
+// ---- split-K for 1x1 / FC shapes: too few output tiles to fill the GPU, long K ------------------------
+// out = st*out + so * sum_s part[s]  (+ bias[channel], ReLU | zero where mask <= 0): the fused epilogue moves here
+__global__ void __launch_bounds__(256) reduce_split_kernel(const float4* __restrict__ part, float4* out, long long elems4,
+                                                           long long stride4, int splits, float st, float so,
+                                                           const float* __restrict__ bias, long long per_channel4, int relu,
+                                                           const float4* __restrict__ mask) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < elems4; i += (long long)gridDim.x * blockDim.x) {
+    float4 s = part[i];
+    for (int k = 1; k < splits; k++) {
+      const float4 v = part[i + k * stride4];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    s.x *= so; s.y *= so; s.z *= so; s.w *= so;
+    if (st != 0.f) { const float4 o = out[i]; s.x += st * o.x; s.y += st * o.y; s.z += st * o.z; s.w += st * o.w; }
+    if (bias) { const float b = __ldg(bias + i / per_channel4); s.x += b; s.y += b; s.z += b; s.w += b; }
+    if (relu) { s.x = fmaxf(s.x, 0.f); s.y = fmaxf(s.y, 0.f); s.z = fmaxf(s.z, 0.f); s.w = fmaxf(s.w, 0.f); }
+    if (mask) {
+      const float4 m = mask[i];
+      if (!(m.x > 0.f)) s.x = 0.f;
+      if (!(m.y > 0.f)) s.y = 0.f;
+      if (!(m.z > 0.f)) s.z = 0.f;
+      if (!(m.w > 0.f)) s.w = 0.f;
+    }
+    out[i] = s;
+  }
+}
+void reduce_split(const float* part, float* out, long long elems, int splits, float st, float so, const float* bias,
+                  long long per_channel, int relu, const float* mask) {
+  const long long e4 = elems / 4;
+  const int grid = (int)std::min<long long>(std::max<long long>(ceil_div<long long>(e4, 256), 1), 8LL * num_sms());
+  reduce_split_kernel<<<grid, 256, 0, state().stream>>>((const float4*)part, (float4*)out, e4, e4, splits, st, so, bias,
+                                                        per_channel / 4, relu, (const float4*)mask);
+  count_launch();
+  CNB_LAUNCH_CHECK("reduce_split");
+}
+// how many K splits a fprop/dgrad launch should use (1 = none): only 1x1 / FC shapes that leave most SMs idle
+int pick_ksplit(const TcParams& p, const ConvGeom& g, long long out_elems) {
+  static const bool off = getenv("CONVNET_B200_NO_SPLITK") && getenv("CONVNET_B200_NO_SPLITK")[0] == '1';
+  if (off || p.x_mode || p.taps != 1 || g.frames != 1 || out_elems % 4 != 0) return 1;
+  if (p.num_tiles * 2 > num_sms() || p.kc_blocks < 8) return 1;
+  const int want = std::min(num_sms() / p.num_tiles, p.kc_blocks / 4);
+  return std::max(want, 1);
+}
 bool want_bf16() { return state().precision == kPrecBF16; }
 inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
 }  // namespace
+
+void bf16_invalidate(const float* ptr) {
+  for (Staged& e : staged_table())
+    if (ptr == nullptr || e.src == ptr) e.valid = false;
+}
+void bf16_release() {
+  if (staged_table().empty()) return;
+  CNB_CUDA_CHECK(cudaStreamSynchronize(state().stream));
+  for (Staged& e : staged_table()) if (e.buf) CNB_CUDA_CHECK(cudaFree(e.buf));
+  staged_table().clear();
+}
+void bf16_stage(const float* ptr, long long n) {
+  if (!want_bf16() || ptr == nullptr || n <= 0 || !aligned16(ptr)) return;
+  std::vector<Staged>& t = staged_table();
+  Staged* slot = nullptr;
+  for (Staged& e : t) if (e.src == ptr) { slot = &e; break; }
+  if (!slot) {
+    if (t.size() >= kMaxStaged) {                                       // recycle the least recently used entry
+      slot = &t[0];
+      for (Staged& e : t) if (e.tick < slot->tick) slot = &e;
+    } else {
+      t.push_back(Staged{ptr, 0, nullptr, 0, false, 0});
+      slot = &t.back();
+    }
+  }
+  const size_t bytes = align_up((size_t)n * 2);
+  if (slot->cap < bytes) {
+    if (slot->buf) { CNB_CUDA_CHECK(cudaStreamSynchronize(state().stream)); CNB_CUDA_CHECK(cudaFree(slot->buf)); }
+    slot->buf = nullptr; slot->cap = 0;
+    CNB_CUDA_CHECK(cudaMalloc((void**)&slot->buf, bytes));
+    slot->cap = bytes;
+  }
+  slot->src = ptr; slot->n = n; slot->tick = ++g_stage_tick;
+  to_bf16(ptr, slot->buf, n);
+  slot->valid = true;
+}
 
 // ---- fprop ---------------------------------------------------------------------------------------
 // `bf` selects bf16 operands (CONVNET_B200_PRECISION=bf16): images and filters are first rounded to bf16 copies in
@@ -805,7 +909,10 @@ static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float*
   if (g.N % 4 != 0 || g.Cout % 4 != 0) return false;                        // TMA stride alignment
   const bool x_mode = g.Cin < 8;                                            // tiny channel counts: taps take the K block
   if (x_mode && (g.kx > 8 || g.ky > 8)) return false;
-  if (bf && (x_mode || g.N % 64 != 0 || g.Cout % 8 != 0 || !aligned16(images) || !aligned16(filters))) return false;
+  if (bf && (x_mode || g.N % 8 != 0 || g.Cout % 8 != 0 || !aligned16(images) || !aligned16(filters))) return false;
+  // few GEMM rows (FC layers at training batch sizes): the call streams the weights once and is HBM-bound on them;
+  // a bf16 staging pass would read them a second time, so such shapes stay on the tf32 path
+  if (bf && (long long)g.N * g.modules * g.frames < 1024) return false;
   TcParams p; fill_common(p, g, e);
   p.BN = pick_bn(g.Cout, e.chunk);
   p.kc_blocks = ceil_div(g.Cin, e.bk);
@@ -814,14 +921,24 @@ static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float*
   p.b_tx_bytes = (uint32_t)p.BN * 128;
   const long long chunks = (long long)p.nb * g.modules * g.frames;
   if (chunks * 4 >= (1LL << 31)) return false;
-  p.total_rows32 = (int)chunks;
   p.total_chunks = p.nbc * g.modules * g.frames;
   p.m_tiles = ceil_div(p.total_chunks, p.cpt);
   p.n_tiles = ceil_div(g.Cout, p.BN);
   p.num_tiles = p.m_tiles * p.n_tiles;
-  p.out = targets + (long long)g.cout0 * g.modules * g.N;
+  float* const out = targets + (long long)g.cout0 * g.modules * g.N;
+  const float* const bias = fuse.bias ? fuse.bias + g.cout0 : nullptr;
+  const long long out_elems = (long long)g.Cout * g.modules * g.N;
+  const int ks = pick_ksplit(p, g, out_elems);
+  if (ks > 1) {
+    p.units_per_split = ceil_div(p.kc_blocks, ks);
+    p.splits = ceil_div(p.kc_blocks, p.units_per_split);
+    p.part_stride = out_elems;
+    p.num_tiles *= p.splits;
+  }
+  const size_t part_bytes = p.splits > 1 ? align_up(sizeof(float) * out_elems * p.splits) : 0;
+  p.out = out;
   p.st = st; p.so = so;
-  p.bias = fuse.bias ? fuse.bias + g.cout0 : nullptr; p.relu = fuse.relu;
+  p.bias = bias; p.relu = fuse.relu;
   p.idesc = ptx::make_idesc(bf ? 1 : 2, true, true, BM, p.BN);
   apply_pair(p, kFprop, e.chunk, 1);
   const int bn_local = p.cta2 ? p.BN / 2 : p.BN;
@@ -830,14 +947,20 @@ static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float*
   const void* img = images + img_off;
   const void* flt = filters;
   const long long taps = (long long)g.kx * g.ky;
+  uint8_t* ws = nullptr;
   if (bf) {
-    const size_t ib = align_up((size_t)g.img_total * 2), fb = align_up((size_t)g.Cout * g.K * 2);
-    uint8_t* ws = (uint8_t*)workspace(ib + fb);
-    to_bf16(images, (__nv_bfloat16*)ws, g.img_total);
-    to_bf16(filters, (__nv_bfloat16*)(ws + ib), (long long)g.Cout * g.K);
-    img = (const __nv_bfloat16*)ws + img_off;
-    flt = ws + ib;
+    const __nv_bfloat16* si = staged(images, g.img_total);
+    const __nv_bfloat16* sf = staged(filters, (long long)g.Cout * g.K);
+    const size_t ib = si ? 0 : align_up((size_t)g.img_total * 2), fb = sf ? 0 : align_up((size_t)g.Cout * g.K * 2);
+    if (part_bytes + ib + fb) ws = (uint8_t*)workspace(part_bytes + ib + fb);
+    if (!si) { to_bf16(images, (__nv_bfloat16*)(ws + part_bytes), g.img_total); si = (const __nv_bfloat16*)(ws + part_bytes); }
+    if (!sf) { to_bf16(filters, (__nv_bfloat16*)(ws + part_bytes + ib), (long long)g.Cout * g.K); sf = (const __nv_bfloat16*)(ws + part_bytes + ib); }
+    img = si + img_off;
+    flt = sf;
+  } else if (part_bytes) {
+    ws = (uint8_t*)workspace(part_bytes);
   }
+  if (p.splits > 1) { p.out = (float*)ws; p.bias = nullptr; p.relu = 0; }   // partial sums; the epilogue moves to reduce_split
   p.a_merged = (allow_merge() && g.frames == 1 && g.N % 128 == 0) ? 1 : 0;
   p.b_merged = (allow_merge() && g.Cout % e.chunk == 0) ? 1 : 0;
   // frames of a 3-D conv start in_frame_step floats apart and see Cin (= Cin3d*kt) channels
@@ -879,6 +1002,7 @@ static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float*
     }
   }
   launch<kFprop>(ma, mb, p);
+  if (p.splits > 1) reduce_split((const float*)ws, out, out_elems, p.splits, st, so, bias, (long long)g.modules * g.N, fuse.relu, nullptr);
   state().last_conv_path = bf ? kPathTcBf16 : kPathTcTf32;
   return true;
 }
@@ -894,13 +1018,13 @@ static bool tc_conv_down_impl(const ConvGeom& g, const float* derivs, const floa
                               const Fuse& fuse, bool bf) {
   const Elem e = elem_for(bf);
   if (g.N % 4 != 0 || g.Cout % 4 != 0 || g.Cout < 8 || g.Cin < 8) return false;
-  if (bf && (g.N % 64 != 0 || g.Cout % 8 != 0 || !aligned16(derivs) || !aligned16(filters))) return false;
+  if (bf && (g.N % 8 != 0 || g.Cout % 8 != 0 || !aligned16(derivs) || !aligned16(filters))) return false;
+  if (bf && (long long)g.N * g.W * g.H < 1024) return false;                 // weight-streaming bound (see tc_conv_up_impl)
   TcParams p; fill_common(p, g, e);
   p.BN = pick_bn(g.Cin, 16);
   p.kc_blocks = ceil_div(g.Cout, e.bk);
   const long long chunks = (long long)p.nb * g.W * g.H;
   if (chunks * 4 >= (1LL << 31) || g.kx > 32 || g.ky > 32) return false;
-  p.total_rows32 = (int)chunks;
   p.total_chunks = p.nbc * g.W * g.H;
   p.m_tiles = ceil_div(p.total_chunks, p.cpt);
   p.n_tiles = ceil_div(g.Cin, p.BN);
@@ -908,19 +1032,34 @@ static bool tc_conv_down_impl(const ConvGeom& g, const float* derivs, const floa
   p.so = so;
   p.b_tx_bytes = (uint32_t)p.BN * 128;
   p.idesc = ptx::make_idesc(bf ? 1 : 2, true, false, BM, p.BN);
+  const bool whole = (g.frames == 1 && g.cin0 == 0 && g.Cin == g.CinT);
+  const long long out_elems = (long long)g.Cin * g.W * g.H * g.N;
+  const int ks = whole ? pick_ksplit(p, g, out_elems) : 1;
+  if (ks > 1) {
+    p.units_per_split = ceil_div(p.kc_blocks, ks);
+    p.splits = ceil_div(p.kc_blocks, p.units_per_split);
+    p.part_stride = out_elems;
+    p.num_tiles *= p.splits;
+  }
+  const size_t part_bytes = p.splits > 1 ? align_up(sizeof(float) * out_elems * p.splits) : 0;
   apply_pair(p, kDgrad, 8, 1);
   const int bn_local = p.cta2 ? p.BN / 2 : p.BN;
   CUtensorMap ma, mb;
   const long long der_off = (long long)g.cout0 * g.modules * g.N;
   const void* der = derivs + der_off;
   const void* flt = filters;
+  uint8_t* ws = nullptr;
   if (bf) {
-    const size_t db = align_up((size_t)g.out_total * 2), fb = align_up((size_t)g.Cout * g.K * 2);
-    uint8_t* ws = (uint8_t*)workspace(db + fb);
-    to_bf16(derivs, (__nv_bfloat16*)ws, g.out_total);
-    to_bf16(filters, (__nv_bfloat16*)(ws + db), (long long)g.Cout * g.K);
-    der = (const __nv_bfloat16*)ws + der_off;
-    flt = ws + db;
+    const __nv_bfloat16* sd = staged(derivs, g.out_total);
+    const __nv_bfloat16* sf = staged(filters, (long long)g.Cout * g.K);
+    const size_t db = sd ? 0 : align_up((size_t)g.out_total * 2), fb = sf ? 0 : align_up((size_t)g.Cout * g.K * 2);
+    if (part_bytes + db + fb) ws = (uint8_t*)workspace(part_bytes + db + fb);
+    if (!sd) { to_bf16(derivs, (__nv_bfloat16*)(ws + part_bytes), g.out_total); sd = (const __nv_bfloat16*)(ws + part_bytes); }
+    if (!sf) { to_bf16(filters, (__nv_bfloat16*)(ws + part_bytes + db), (long long)g.Cout * g.K); sf = (const __nv_bfloat16*)(ws + part_bytes + db); }
+    der = sd + der_off;
+    flt = sf;
+  } else if (part_bytes) {
+    ws = (uint8_t*)workspace(part_bytes);
   }
   p.a_merged = (allow_merge() && g.frames == 1 && g.N % 128 == 0) ? 1 : 0;
   if (p.a_merged) {
@@ -933,8 +1072,11 @@ static bool tc_conv_down_impl(const ConvGeom& g, const float* derivs, const floa
     if (!make_map(&mb, flt, e, 3, dims, str, box, false)) return false;
   }
   float* out = targets + (long long)g.cin0 * g.H * g.W * g.N;
-  const bool whole = (g.frames == 1 && g.cin0 == 0 && g.Cin == g.CinT);
-  if (whole) {
+  if (whole && p.splits > 1) {
+    p.st = 0.f; p.out = (float*)ws; p.mask = nullptr;
+    launch<kDgrad>(ma, mb, p);
+    reduce_split((const float*)ws, out, out_elems, p.splits, st, so, nullptr, 1, 0, fuse.relu_mask);
+  } else if (whole) {
     p.st = st; p.out = out; p.mask = fuse.relu_mask ? fuse.relu_mask + (long long)g.cin0 * g.H * g.W * g.N : nullptr;
     launch<kDgrad>(ma, mb, p);
   } else {
@@ -964,7 +1106,8 @@ static bool tc_conv_outp_impl(const ConvGeom& g, const float* images, const floa
   if (g.N % 4 != 0 || g.Cout < 8) return false;
   const bool x_mode = g.Cin < 8;
   if (x_mode && (g.kx > 8 || g.ky > 8)) return false;
-  if (bf && (x_mode || g.N % 64 != 0 || !aligned16(images) || !aligned16(derivs))) return false;
+  if (bf && (x_mode || g.N % 8 != 0 || !aligned16(images) || !aligned16(derivs))) return false;
+  if (bf && (long long)g.N * g.modules * g.frames < 1024) return false;      // output-write bound: nothing to gain
   TcParams p; fill_common(p, g, e);
   p.kc_blocks = 0;
   p.m_tiles = ceil_div(g.Cout, BM);
@@ -998,12 +1141,14 @@ static bool tc_conv_outp_impl(const ConvGeom& g, const float* images, const floa
   const size_t part_bytes = p.splits > 1 ? align_up(sizeof(float) * elems * p.splits) : 0;
   uint8_t* ws = nullptr;
   if (bf) {
-    const size_t ib = align_up((size_t)g.img_total * 2), db = align_up((size_t)g.out_total * 2);
-    ws = (uint8_t*)workspace(part_bytes + ib + db);
-    to_bf16(images, (__nv_bfloat16*)(ws + part_bytes), g.img_total);
-    to_bf16(derivs, (__nv_bfloat16*)(ws + part_bytes + ib), g.out_total);
-    img = (const __nv_bfloat16*)(ws + part_bytes) + img_off;
-    der = (const __nv_bfloat16*)(ws + part_bytes + ib) + der_off;
+    const __nv_bfloat16* si = staged(images, g.img_total);
+    const __nv_bfloat16* sd = staged(derivs, g.out_total);
+    const size_t ib = si ? 0 : align_up((size_t)g.img_total * 2), db = sd ? 0 : align_up((size_t)g.out_total * 2);
+    if (part_bytes + ib + db) ws = (uint8_t*)workspace(part_bytes + ib + db);
+    if (!si) { to_bf16(images, (__nv_bfloat16*)(ws + part_bytes), g.img_total); si = (const __nv_bfloat16*)(ws + part_bytes); }
+    if (!sd) { to_bf16(derivs, (__nv_bfloat16*)(ws + part_bytes + ib), g.out_total); sd = (const __nv_bfloat16*)(ws + part_bytes + ib); }
+    img = si + img_off;
+    der = sd + der_off;
   } else if (part_bytes) {
     ws = (uint8_t*)workspace(part_bytes);
   }

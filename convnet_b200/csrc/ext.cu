@@ -3,6 +3,7 @@
 
 #include "../../include/convnet_b200_ext.h"
 #include "common.cuh"
+#include "conv_kernels.h"
 
 namespace cnb {
 
@@ -75,11 +76,14 @@ int convnet_b200_get_conv_precision(void) { return state().precision; }
 void convnet_b200_fuse_next(const float* bias, int relu, const float* relu_mask) {
   state().fuse.bias = bias; state().fuse.relu = relu; state().fuse.relu_mask = relu_mask;
 }
+void convnet_b200_bf16_stage(const float* ptr, long long n) { bf16_stage(ptr, n); }
+void convnet_b200_bf16_invalidate(const float* ptr) { bf16_invalidate(ptr); }
 int convnet_b200_last_conv_path(void) { return state().last_conv_path; }
 unsigned long long convnet_b200_launch_count(void) { return state().launches; }
 void convnet_b200_reset_launch_count(void) { state().launches = 0; }
 void convnet_b200_release_workspace(void) {
   State& s = state();
+  bf16_release();
   if (s.ws) {
     CNB_CUDA_CHECK(cudaStreamSynchronize(s.stream));
     CNB_CUDA_CHECK(cudaFree(s.ws));

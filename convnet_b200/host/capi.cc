@@ -39,7 +39,8 @@ API long long cnb_net_input_floats(void* p) { return (long long)((NetHandle*)p)-
 API int* cnb_net_labels(void* p) { return ((NetHandle*)p)->net->OutputLayer().GetLabels(); }
 API float* cnb_net_output(void* p) { return ((NetHandle*)p)->net->OutputLayer().GetState().GetDevData(); }
 API int cnb_net_num_classes(void* p) { return ((NetHandle*)p)->net->OutputLayer().GetState().GetCols(); }
-API float* cnb_net_params(void* p) { return ((NetHandle*)p)->net->Parameters().GetDevData(); }
+// the caller may write through this pointer: staged bf16 copies of the weights are dropped
+API float* cnb_net_params(void* p) { ((NetHandle*)p)->net->InvalidateStaging(); return ((NetHandle*)p)->net->Parameters().GetDevData(); }
 API float* cnb_net_grads(void* p) { return ((NetHandle*)p)->net->GradParameters().GetDevData(); }
 API float* cnb_net_layer_state(void* p, int i) { return ((NetHandle*)p)->net->Layers()[i]->GetState().GetDevData(); }
 API long long cnb_net_layer_floats(void* p, int i) { return (long long)((NetHandle*)p)->net->Layers()[i]->GetState().GetNumEls(); }

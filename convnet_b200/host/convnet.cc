@@ -203,7 +203,15 @@ ConvNet::ConvNet(const ModelConfig& model, int batch_size) : model_(model), batc
   }
 }
 
+// Parameters were (or may have been) written outside EdgeWithWeight::UpdateWeights: forget every staged bf16 copy.
+void ConvNet::InvalidateStaging() {
+  convnet_b200_bf16_invalidate(nullptr);
+  for (Edge* e : edges_)
+    if (EdgeWithWeight* w = dynamic_cast<EdgeWithWeight*>(e)) w->MarkWeightsDirty();
+}
+
 ConvNet::~ConvNet() {
+  convnet_b200_bf16_invalidate(nullptr);                     // the buffers go away; a later net may get the same addresses
   for (Edge* e : edges_) delete e;
   for (Layer* l : layers_) delete l;
 }
@@ -236,6 +244,7 @@ void ConvNet::AllocateMemory() {
     edges_[i]->Initialize(model_.seed + 17 * (unsigned)i);
   }
   HOST_CUDA_CHECK(cudaStreamSynchronize(Matrix::Stream()));
+  InvalidateStaging();
 }
 
 void ConvNet::Fprop(bool train) {                            // convnet.cc:377-388
@@ -313,7 +322,10 @@ void ConvNet::SetDataParallel(DataParallelSync* dp, size_t bucket_floats) {
   dp_ = dp;
   buckets_ = PlanBuckets(edge_offset_, edge_size_, bucket_floats);
 }
-void ConvNet::BroadcastParameters() { if (dp_) dp_->Broadcast(parameters_.GetDevData(), parameters_.GetNumEls()); }
+void ConvNet::BroadcastParameters() {
+  if (dp_) dp_->Broadcast(parameters_.GetDevData(), parameters_.GetNumEls());
+  InvalidateStaging();
+}
 
 double ConvNet::FlopsFprop() const {
   double f = 0;
@@ -331,6 +343,7 @@ float GradChecker::LossAt(Matrix& w, size_t index, float value) { return (float)
 
 double GradChecker::LossAtD(Matrix& w, size_t index, float value) {
   w.WriteValue(index, value);
+  InvalidateStaging();
   Fprop(false);
   // per-image cross-entropy on the device, summed in double on the host: the finite difference of two ~O(batch)
   // losses must not lose the 1e-3-sized signal to fp32 summation noise
@@ -379,6 +392,7 @@ std::vector<GradCheckResult> GradChecker::Run(unsigned seed) {
         const double e1 = LossAtD(w, i, val + epsilon);
         const double e2 = LossAtD(w, i, val - epsilon);
         w.WriteValue(i, val);
+        InvalidateStaging();
         const float numeric = (float)((e1 - e2) / (batch_size_ * 2.0 * epsilon));
         const float diff = analytical[i] - numeric, scale = (analytical[i] + numeric) / 2;
         if (!(scale == 0 && diff == 0)) { diff_sum += std::fabs(diff / scale); non_zero++; }

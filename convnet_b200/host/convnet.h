@@ -111,6 +111,7 @@ class ConvNet {
   float GetLoss();                                              // sum of per-image CE (synchronises)
   void SetDataParallel(DataParallelSync* dp, size_t bucket_floats);
   void BroadcastParameters();
+  void InvalidateStaging();                                     // after any write to the parameters from outside UpdateWeights
 
   Layer& InputLayer() { return *layers_.front(); }
   Layer& OutputLayer() { return *layers_.back(); }

@@ -72,8 +72,27 @@ void EdgeWithWeight::SetHistoryMemory(Matrix& p) {
   }
 }
 
+void EdgeWithWeight::StageForUp(Matrix& input) {
+  deriv_staged_ = false;
+  if (convnet_b200_get_conv_precision() != 2) return;
+  if (bf_up_ == 1 || bf_outer_ == 1) convnet_b200_bf16_stage(input.GetDevData(), (long long)input.GetNumEls());
+  if ((bf_up_ == 1 || bf_down_ == 1) && weights_dirty_) {
+    convnet_b200_bf16_stage(weights_.GetDevData(), (long long)weights_.GetNumEls());
+    weights_dirty_ = false;
+  }
+}
+void EdgeWithWeight::StageForBprop(Matrix& deriv_output) {
+  if (deriv_staged_ || convnet_b200_get_conv_precision() != 2) return;
+  if (bf_outer_ == 1 || bf_down_ == 1) convnet_b200_bf16_stage(deriv_output.GetDevData(), (long long)deriv_output.GetNumEls());
+  deriv_staged_ = true;
+}
+void EdgeWithWeight::NoteUp() { bf_up_ = convnet_b200_last_conv_path() == 2 ? 1 : 0; }
+void EdgeWithWeight::NoteDown() { bf_down_ = convnet_b200_last_conv_path() == 2 ? 1 : 0; }
+void EdgeWithWeight::NoteOuter() { bf_outer_ = convnet_b200_last_conv_path() == 2 ? 1 : 0; }
+
 void EdgeWithWeight::UpdateWeights() {                       // src/edge_with_weight.cc:96-107 + optimizer.cc:174-200
   num_grads_received_ = 0;
+  weights_dirty_ = true;
   const OptimizerConfig& wo = config_.weight_optimizer;
   cnb_sgd_momentum(weights_.GetDevData(), hist_weights_.GetDevData(), grad_weights_.GetDevData(),
                    (long long)weights_.GetNumEls(), wo.epsilon, wo.momentum, wo.l2_decay);
@@ -152,12 +171,14 @@ void ConvEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool tra
   const float scale_targets = overwrite ? 0 : 1;
   const int mods = num_modules_y_ * num_modules_x_ * num_modules_t_;
   const bool fused = fuse_relu_ && CanFuseReLU();        // bias (+ReLU of the destination layer) in the conv epilogue
+  StageForUp(input);
   if (image_size_t_ == 1) {
     if (fused) convnet_b200_fuse_next(bias_.GetDevData(), 1, nullptr);
     Matrix::ConvUp(input, weights_, output, conv_desc_, scale_targets);
   } else {
     Matrix::Conv3DUp(input, weights_, output, conv_desc_, scale_targets);
   }
+  NoteUp();
   if (!has_no_bias_ && !fused) {
     if (shared_bias_ && image_size_t_ == 1) {
       output.Reshape(-1, conv_desc_.num_output_channels);
@@ -180,9 +201,11 @@ void ConvEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool tra
 void ConvEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input,
                            bool overwrite) {                 // :172-181
   const float scale_targets = overwrite ? 0 : 1;
+  StageForBprop(deriv_output);
   if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());      // ReLU' of the source layer
   if (image_size_t_ == 1) Matrix::ConvDown(deriv_output, weights_, deriv_input, conv_desc_, scale_targets);
   else Matrix::Conv3DDown(deriv_output, weights_, deriv_input, conv_desc_, scale_targets);
+  NoteDown();
 }
 
 void ConvEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {   // :183-245
@@ -190,11 +213,13 @@ void ConvEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {   // :183-245
   const int scale_targets = GetNumGradsReceived() > 0 ? 1 : 0;
   const float scale = scale_gradients_ / batch_size;
   const int mods = num_modules_y_ * num_modules_x_ * num_modules_t_;
+  StageForBprop(deriv_output);
   if (image_size_t_ == 1) {
     Matrix::ConvOutp(input, deriv_output, grad_weights_, conv_desc_, partial_sum_y_, partial_sum_x_, scale_targets, scale);
   } else {
     Matrix::Conv3DOutp(input, deriv_output, grad_weights_, conv_desc_, scale_targets, scale);
   }
+  NoteOuter();
   if (!has_no_bias_) {
     if (shared_bias_ && image_size_t_ == 1) {
       // the reference sums in two steps through a temp (:212-218); one deterministic pass here
@@ -260,16 +285,20 @@ void FCEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train
   Shape4D si = input.GetShape4D(), so = output.GetShape4D();
   View(input, output);
   const bool fused = fuse_relu_ && !has_no_bias_;
+  StageForUp(input);
   if (fused) convnet_b200_fuse_next(bias_.GetDevData(), 1, nullptr);
   Matrix::ConvUp(input, weights_, output, desc_, overwrite ? 0 : 1);     // output = input * W^T
+  NoteUp();
   if (!has_no_bias_ && !fused) output.AddRowVec(bias_);
   input.GetShape4D() = si; output.GetShape4D() = so;
 }
 void FCEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) {
   Shape4D si = deriv_input.GetShape4D(), so = deriv_output.GetShape4D();
   View(deriv_input, deriv_output);
+  StageForBprop(deriv_output);
   if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
   Matrix::ConvDown(deriv_output, weights_, deriv_input, desc_, overwrite ? 0 : 1);
+  NoteDown();
   deriv_input.GetShape4D() = si; deriv_output.GetShape4D() = so;
 }
 void FCEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {                          // fc_edge.cc:69-81
@@ -277,7 +306,9 @@ void FCEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {                
   const int scale_targets = GetNumGradsReceived() > 0 ? 1 : 0;
   Shape4D si = input.GetShape4D(), so = deriv_output.GetShape4D();
   View(input, deriv_output);
+  StageForBprop(deriv_output);
   Matrix::ConvOutp(input, deriv_output, grad_weights_, desc_, 0, 0, scale_targets, scale_gradients_ / batch_size);
+  NoteOuter();
   if (!has_no_bias_) deriv_output.SumRows(grad_bias_, scale_targets, scale_gradients_ / batch_size);
   input.GetShape4D() = si; deriv_output.GetShape4D() = so;
   IncrementNumGradsReceived();
@@ -307,8 +338,10 @@ void ConvOneToOneEdge::SetGradMemory(Matrix& p) {
 void ConvOneToOneEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) {   // :56-73
   const int batch_size = input.GetRows();
   const bool fused = fuse_relu_ && !has_no_bias_;
+  StageForUp(input);
   if (fused) convnet_b200_fuse_next(bias_.GetDevData(), 1, nullptr);
   Matrix::ConvUp(input, weights_, output, desc_, overwrite ? 0 : 1);
+  NoteUp();
   if (!has_no_bias_ && !fused) {
     output.Reshape(-1, num_output_channels_);
     output.AddRowVec(bias_);
@@ -317,13 +350,17 @@ void ConvOneToOneEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, 
 }
 void ConvOneToOneEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input,
                                    bool overwrite) {
+  StageForBprop(deriv_output);
   if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
   Matrix::ConvDown(deriv_output, weights_, deriv_input, desc_, overwrite ? 0 : 1);
+  NoteDown();
 }
 void ConvOneToOneEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {                        // :87-102
   const int batch_size = input.GetRows();
   const int scale_targets = GetNumGradsReceived() > 0 ? 1 : 0;
+  StageForBprop(deriv_output);
   Matrix::ConvOutp(input, deriv_output, grad_weights_, desc_, 0, 0, scale_targets, scale_gradients_ / batch_size);
+  NoteOuter();
   if (!has_no_bias_) {
     deriv_output.Reshape(-1, num_output_channels_);
     deriv_output.SumRows(grad_bias_, scale_targets, scale_gradients_ / batch_size);

@@ -116,12 +116,24 @@ class EdgeWithWeight : public Edge {
   void IncrementNumGradsReceived() { num_grads_received_++; }
   void NotifyStart() { num_grads_received_ = 0; }
   virtual int FanIn() const = 0;
+  // bf16 mode (convnet_b200_set_conv_precision(2)): each tensor this edge feeds to two conv calls of a step is converted
+  // once through convnet_b200_bf16_stage — the input (fprop + wgrad), the output derivative (wgrad + dgrad) and the
+  // weights (fprop + dgrad, re-staged after every update).  Which calls really run in bf16 is learnt from
+  // convnet_b200_last_conv_path() during the first step (FC-shaped calls stay on tf32 and are not staged).
+  void MarkWeightsDirty() { weights_dirty_ = true; }
 
  protected:
+  void StageForUp(Matrix& input);
+  void StageForBprop(Matrix& deriv_output);
+  void NoteUp();
+  void NoteDown();
+  void NoteOuter();
   Matrix weights_, grad_weights_, bias_, grad_bias_, hist_weights_, hist_bias_;
   bool has_no_bias_;
   float scale_gradients_;
   int num_grads_received_;
+  int bf_up_ = -1, bf_down_ = -1, bf_outer_ = -1;        // -1 unknown, 0 tf32 / fp32 path, 1 bf16 path
+  bool weights_dirty_ = true, deriv_staged_ = false;
 };
 
 class ConvEdge : public EdgeWithWeight {

@@ -72,6 +72,8 @@ SIGNATURES = {
     "convnet_b200_last_conv_path": [],
     "convnet_b200_launch_count": [],
     "convnet_b200_fuse_next": [FP, I, FP],
+    "convnet_b200_bf16_stage": [FP, ct.c_longlong],
+    "convnet_b200_bf16_invalidate": [FP],
     "convnet_b200_reset_launch_count": [],
     "convnet_b200_release_workspace": [],
     "cnb_add_channel_bias": [FP, FP, ct.c_longlong, I],

@@ -54,6 +54,16 @@ void convnet_b200_release_workspace(void);
  * Pass NULL / 0 for the parts not wanted.  Calls that cannot fuse (3-D dgrad) apply the same maths in a second pass. */
 void convnet_b200_fuse_next(const float* bias, int relu, const float* relu_mask);
 
+/* bf16 operand staging (precision mode 2 only; no-ops in the other modes).  In bf16 mode every conv call first rounds
+ * its two fp32 operands to bf16 copies.  A caller that knows a tensor stays unchanged across several conv calls
+ * (the layer input: fprop + wgrad; the output derivative: wgrad + dgrad; the weights: fprop + dgrad) can have it
+ * converted ONCE: convnet_b200_bf16_stage(ptr, n) converts the n floats at ptr now (stream-ordered) and conv calls
+ * that receive exactly `ptr` as an operand use that copy until the next _stage / _invalidate of the same pointer.
+ * The CALLER owns coherence: after writing to a staged tensor it must stage it again or invalidate it.
+ * convnet_b200_bf16_invalidate(NULL) forgets every staged tensor. */
+void convnet_b200_bf16_stage(const float* ptr, long long n);
+void convnet_b200_bf16_invalidate(const float* ptr);
+
 /* ---- steps either side of the conv ops that the Edge layer sequences ------------
  * (in the reference these are libcudamat.so calls:
  *  add_row_vec cudamat.cu:1064, sum_by_axis :1614, lower_bound_scalar :1426,

@@ -49,10 +49,11 @@ def test_analytic_gradients_agree_between_fp32_and_tf32(env):
     assert ((a - b).norm() / a.norm()).item() < 5e-2
 
 
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
 @pytest.mark.parametrize("model,batch,classes", [("tiny", 32, 10), ("lenet", 100, 10)])
-def test_training_reduces_the_loss(env, model, batch, classes):
+def test_training_reduces_the_loss(env, model, batch, classes, mode):
     torch, lib, net = env
-    lib.set_precision("tf32")
+    lib.set_precision(mode)
     n = net.Net(model, batch, seed=1)
     g = torch.Generator(device="cuda").manual_seed(0)
     n.input_tensor().normal_(generator=g)
@@ -64,9 +65,10 @@ def test_training_reduces_the_loss(env, model, batch, classes):
     assert min(losses[30:]) < 0.8 * losses[0], losses[::6]     # SGD on one fixed batch drives the loss down
 
 
-def test_alexnet_step_small_batch(env):
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_alexnet_step_small_batch(env, mode):
     torch, lib, net = env
-    lib.set_precision("tf32")
+    lib.set_precision(mode)
     n = net.Net("alexnet", 8, seed=1)
     assert n.num_params == 104321024                             # 104,321,000 + 128-float padding per edge
     assert abs(n.flops_train / 8 / 1e9 - 11.87) < 0.01
@@ -163,7 +165,7 @@ def test_backprop_matches_float64_autograd(env, model):
     """Every backward op of the chain (wgrad, dgrad, bias grad, max/avg-pool undo, response-norm undo, ReLU/softmax
     derivatives) against an independent float64 PyTorch autograd model with the same parameters."""
     torch, lib, net = env
-    for mode, tol in (("fp32", 2e-5), ("tf32", 5e-2)):
+    for mode, tol in (("fp32", 2e-5), ("tf32", 5e-2), ("bf16", 1.5e-1)):
         lib.set_precision(mode)
         batch = 32
         n = net.Net(model, batch, seed=7)
@@ -173,7 +175,7 @@ def test_backprop_matches_float64_autograd(env, model):
         n.fprop(False); n.bprop()
         loss = n.loss()
         ref_loss, params = _torch_net(torch, n, batch, model)
-        assert abs(loss - ref_loss) / ref_loss < (1e-5 if mode == "fp32" else 2e-3)
+        assert abs(loss - ref_loss) / ref_loss < {"fp32": 1e-5, "tf32": 2e-3, "bf16": 1e-2}[mode]
         G = n.grads_tensor().double()
         edges = n.edges()
         for i, (w, b, K) in params.items():

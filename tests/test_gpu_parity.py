@@ -6,6 +6,8 @@ Tolerances (stated once, used everywhere):
   FP32 mode (CUDA-core fp32)            : 1e-4  — the reference's own bar (py/test_conv.py:387)
   TF32 mode (tcgen05 kind::tf32)        : 5e-3  — the tensor core reads the fp32 operands' top 19 bits
                                                    (10-bit mantissa, truncated), fp32 accumulate; measured 2-3.5e-3
+  BF16 mode (tcgen05 kind::f16, bf16)   : 2.5e-2 — operands rounded to bf16 (8-bit mantissa, nearest even) by the
+                                                   staging pass, fp32 accumulate; measured 0.6-1.1e-2
   max-pool values                       : bit-exact
   avg-pool / pool-undo / response-norm  : 1e-4  (rnorm uses __powf like the reference GPU build)
 """
@@ -18,7 +20,7 @@ from oracle_lib import Diff
 
 pytestmark = pytest.mark.gpu
 
-TOL = {"fp32": 1e-4, "tf32": 5e-3}
+TOL = {"fp32": 1e-4, "tf32": 5e-3, "bf16": 2.5e-2}
 TOL_MEM = 1e-4
 
 
@@ -50,7 +52,7 @@ def gpu():
 # ------------------------------------------------------------------------------------------
 # 1. golden vectors produced by the reference's py/conv_cpu.py
 # ------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 @pytest.mark.parametrize("name", GOLDEN_2D)
 def test_golden_conv2d(gpu, name, mode):
     gpu.lib.set_precision(mode)
@@ -96,7 +98,7 @@ def test_golden_pool_rnorm2d(gpu, name):
         assert Diff(out.asarray(), g["rnormUndo" + tag]) < TOL_MEM
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 @pytest.mark.parametrize("name", GOLDEN_3D)
 def test_golden_3d(gpu, name, mode):
     gpu.lib.set_precision(mode)
@@ -141,6 +143,8 @@ CONV_CASES = {
     "cin8_cout16": (32, 12, 12, 8, 16, 3, 3, 1, 1, 1, 1),         # one K block, mostly zero-filled
     "cin24_s2": (32, 6, 6, 24, 16, 3, 3, 2, 2, 1, 1),
     "cin16_1x1": (32, 6, 6, 16, 24, 1, 1, 1, 1, 0, 0),
+    "fc_splitk": (128, 1, 1, 2048, 512, 1, 1, 1, 1, 0, 0),        # FC: 2 output tiles, 64 K blocks -> split-K + reduce
+    "fc_splitk_b32": (32, 1, 1, 1024, 256, 1, 1, 1, 1, 0, 0),     # partial m-tile with split-K
 }
 
 
@@ -172,7 +176,7 @@ def _oracle_conv(oracle, case):
     return _ORACLE_CACHE[case]
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 @pytest.mark.parametrize("case", sorted(CONV_CASES))
 def test_conv_vs_oracle(gpu, oracle, case, mode):
     gpu.lib.set_precision(mode)
@@ -202,9 +206,16 @@ def test_tensor_core_path_is_taken(gpu):
     assert gpu.lib.last_conv_path() == "tcgen05-tf32"
     out = gpu.new(*filters.shape, fsh); gpu.cg.convOutp(gi, gd, out, d)
     assert gpu.lib.last_conv_path() == "tcgen05-tf32"
+    gpu.lib.set_precision("bf16")
+    out = gpu.new(ish[0], derivs.shape[1], tsh); gpu.cg.convUp(gi, gf, out, d)
+    assert gpu.lib.last_conv_path() == "tcgen05-bf16"
+    out = gpu.new(*images.shape, ish); gpu.cg.convDown(gd, gf, out, d)
+    assert gpu.lib.last_conv_path() == "tcgen05-bf16"
+    out = gpu.new(*filters.shape, fsh); gpu.cg.convOutp(gi, gd, out, d)
+    assert gpu.lib.last_conv_path() == "tcgen05-bf16"
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 def test_conv_scale_targets_semantics(gpu, oracle, mode):
     gpu.lib.set_precision(mode)
     d, ish, fsh, tsh, images, filters, derivs = _conv_case((32, 10, 10, 16, 32, 3, 3, 1, 1, 1, 1))
@@ -222,7 +233,7 @@ def test_conv_scale_targets_semantics(gpu, oracle, mode):
     assert Diff(out.asarray(), ref) < TOL[mode]
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 def test_conv_channel_subranges(gpu, oracle, mode):
     """input/output channel slices (cudamat_conv_gemm.cu:607-613)."""
     gpu.lib.set_precision(mode)
@@ -381,7 +392,7 @@ FULL = {
 }
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 @pytest.mark.parametrize("case", sorted(FULL))
 def test_full_size_adjoint_identity(gpu, case, mode):
     """<convUp(x,w), d> == <x, convDown(d,w)> == <w, convOutp(x,d)> at the BASELINE layer sizes:
@@ -404,7 +415,7 @@ def test_full_size_adjoint_identity(gpu, case, mode):
     b = torch.dot(dn.storage.double(), x.storage.double()).item()
     c = torch.dot(dw.storage.double(), w.storage.double()).item()
     scale = np.sqrt(float(up.storage.numel()))          # |<u,d>| ~ sqrt(n) * sigma_u * sigma_d
-    tol = 5e-3 if mode == "fp32" else 5e-2
+    tol = {"fp32": 5e-3, "tf32": 5e-2, "bf16": 1.5e-1}[mode]
     assert torch.isfinite(up.storage).all() and torch.isfinite(dn.storage).all() and torch.isfinite(dw.storage).all()
     assert abs(a - b) / scale < tol and abs(a - c) / scale < tol, (a, b, c, scale)
 
@@ -471,7 +482,7 @@ def test_elementwise_helpers(gpu):
     assert torch.allclose(w, w2, atol=1e-6) and torch.allclose(h, h2, atol=1e-6)
 
 
-@pytest.mark.parametrize("mode", ["fp32", "tf32"])
+@pytest.mark.parametrize("mode", ["fp32", "tf32", "bf16"])
 def test_fused_epilogues(gpu, oracle, mode):
     """convnet_b200_fuse_next: bias + ReLU in the fprop epilogue, ReLU' mask in dgrad / pool-undo epilogues must equal the
     unfused sequence (conv -> AddRowVec -> LowerBound(0); conv -> ApplyDerivativeOfActivation)."""
@@ -509,3 +520,29 @@ def test_fused_epilogues(gpu, oracle, mode):
     out = gpu.nan(*images.shape, ish)
     L.convnet_b200_fuse_next(None, 0, gs.ptr); gpu.cg.MaxPoolUndo(gpim, gg, mx, out, pd)
     assert Diff(out.asarray(), ref) < TOL_MEM
+
+
+@pytest.mark.parametrize("mode", ["tf32", "bf16"])
+def test_split_k_fused_epilogues(gpu, oracle, mode):
+    """FC-shaped calls leave most SMs idle, so their K loop is split across CTAs and a second kernel reduces the partial
+    sums; bias + ReLU (fprop), the ReLU' mask (dgrad) and scaleTargets then ride in that reduction kernel."""
+    torch = gpu.torch
+    gpu.lib.set_precision(mode)
+    L = gpu.lib.load()
+    d, ish, fsh, tsh, images, filters, derivs = _conv_case((128, 1, 1, 2048, 512, 1, 1, 1, 1, 0, 0))
+    N, Cout = ish[0], 512
+    gi, gf, gd = gpu.up(images, ish), gpu.up(filters, fsh), gpu.up(derivs, tsh)
+    r = np.random.RandomState(4)
+    bias = torch.from_numpy(r.randn(Cout).astype(np.float32)).cuda()
+    ref = Z(*derivs.shape); oracle.convUp(images, filters, ref, ish, fsh, tsh, d)
+    ref = np.maximum(ref + bias.cpu().numpy()[None, :], 0)
+    out = gpu.nan(N, derivs.shape[1], tsh)
+    L.convnet_b200_fuse_next(bias.data_ptr(), 1, None); gpu.cg.convUp(gi, gf, out, d)
+    assert Diff(out.asarray(), ref) < 2 * TOL[mode]
+    state = F(r.randn(*images.shape)); gs = gpu.up(state, ish)
+    init = F(r.randn(*images.shape))
+    ref = init.copy(order="F"); oracle.convDown(derivs, filters, ref, tsh, fsh, ish, d, 1.0)     # scaleTargets = 1
+    ref = np.where(state > 0, ref, 0).astype(np.float32)
+    out = gpu.up(init, ish)
+    L.convnet_b200_fuse_next(None, 0, gs.ptr); gpu.cg.convDown(gd, gf, out, d, 1)
+    assert Diff(out.asarray(), ref) < 2 * TOL[mode]
