@@ -278,7 +278,30 @@ __global__ void reduce_partials_kernel(const float* __restrict__ part, float* ou
   }
 }
 
+// groups == 1, everything 16-byte aligned: four floats per thread, no index arithmetic
+__global__ void __launch_bounds__(256) reduce_partials_v4_kernel(const float4* __restrict__ part, float4* out, long long elems4,
+                                                                 int per, float st, float so) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < elems4; i += (long long)gridDim.x * blockDim.x) {
+    float4 s = part[i];
+    for (int j = 1; j < per; j++) {
+      const float4 v = part[i + j * elems4];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+    s.x *= so; s.y *= so; s.z *= so; s.w *= so;
+    if (st != 0.f) { const float4 o = out[i]; s.x += st * o.x; s.y += st * o.y; s.z += st * o.z; s.w += st * o.w; }
+    out[i] = s;
+  }
+}
+
 void reduce_partials(const float* part, float* out, long long elems, int groups, int per, float st, float so) {
+  if (groups == 1 && elems % 4 == 0 && ((reinterpret_cast<uintptr_t>(part) | reinterpret_cast<uintptr_t>(out)) & 15) == 0) {
+    const long long e4 = elems / 4;
+    const int blocks = (int)std::min<long long>(std::max<long long>(ceil_div<long long>(e4, 256), 1), 8LL * num_sms());
+    reduce_partials_v4_kernel<<<blocks, 256, 0, state().stream>>>((const float4*)part, (float4*)out, e4, per, st, so);
+    count_launch();
+    CNB_LAUNCH_CHECK("reduce_partials");
+    return;
+  }
   const long long total = elems * groups;
   const int blocks = (int)std::min<long long>(ceil_div<long long>(total, 256), 8 * 148);
   reduce_partials_kernel<<<blocks, 256, 0, state().stream>>>(part, out, elems, groups, per, st, so);

@@ -57,6 +57,7 @@ struct TcParams {
   // wgrad: the N tile is (x_ct channels) x (ky rows) x 8 taps, reduced over ALL modules at once.
   int x_mode, x_yblocks, x_ct;
   uint32_t b_tx_bytes;              // bytes the B-operand TMA(s) of one stage actually deliver
+  int b_rows;                       // B stage size in 128-byte rows (MN-major B: whole chunks, so >= the columns used)
   // merged requests: when N % 128 == 0 (2-D) the four 32-image chunks of an m-tile are one box over a
   // (32, ..., N/32, ...) view of the tensor; when Cout % 32 == 0 the BN/32 filter chunks are one box likewise.
   int a_merged, b_merged;
@@ -200,7 +201,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   constexpr bool cta2 = PAIR;
   const int rank = cta2 ? (int)ptx::cluster_ctarank() : 0;          // 0 = leader of the pair
   const int bn_local = cta2 ? p.BN / 2 : p.BN;                      // B columns / rows this CTA stages
-  const uint32_t b_stage_bytes = (uint32_t)bn_local * 128;
+  const uint32_t b_stage_bytes = (uint32_t)p.b_rows * 128;
   uint8_t* smemA = smem;
   uint8_t* smemB = smem + (size_t)p.stages * kAStageBytes;
   SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smemB + (size_t)p.stages * b_stage_bytes);
@@ -308,7 +309,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (p.b_merged) {                // dims (o_lo, c, o_hi, tap)
                   lda4(&mapB, b, 0, cb * p.bk, o0 >> p.chunk_shift, tap);
                 } else {
-                  for (int j = 0; j < (bn_local >> p.chunk_shift); j++)
+                  for (int j = 0; j < ((bn_local + p.chunk - 1) >> p.chunk_shift); j++)   // a last partial chunk loads whole
                     lda3(&mapB, b + j * (p.bk * 128), o0 + j * p.chunk, tap, cb * p.bk);
                 }
                 end_stage();
@@ -666,10 +667,10 @@ int pick_stages(int bn) {
 
 template <int OP>
 void launch(const CUtensorMap& a, const CUtensorMap& b, TcParams& p) {
-  const int bn_local = p.cta2 ? p.BN / 2 : p.BN;
-  p.stages = pick_stages(bn_local);
+  if (p.b_rows == 0) p.b_rows = p.cta2 ? p.BN / 2 : p.BN;
+  p.stages = pick_stages(p.b_rows);
   p.tmem_cols = tmem_cols_for(p.BN);
-  const size_t smem = smem_bytes_for(bn_local, p.stages);
+  const size_t smem = smem_bytes_for(p.b_rows, p.stages);
   static bool attr_set = false;
   if (!attr_set) {
     CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<OP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -738,7 +739,7 @@ void fill_common(TcParams& p, const ConvGeom& g, const Elem& e) {
   p.kx = g.kx; p.ky = g.ky; p.sx = g.sx; p.sy = g.sy; p.px = g.px; p.py = g.py; p.taps = g.kx * g.ky;
   p.frames = g.frames; p.frame0 = 0;
   p.splits = 1; p.units_per_split = 0; p.part_stride = 0;
-  p.x_mode = 0; p.x_yblocks = 0; p.x_ct = 0; p.b_tx_bytes = 0;
+  p.x_mode = 0; p.x_yblocks = 0; p.x_ct = 0; p.b_tx_bytes = 0; p.b_rows = 0;
   p.a_merged = 0; p.b_merged = 0;
   p.cta2 = 0; p.m_groups = 0;
   static const int dbg = getenv("CONVNET_B200_TC_DEBUG") ? atoi(getenv("CONVNET_B200_TC_DEBUG")) : 0;
@@ -915,6 +916,8 @@ static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float*
   if (bf && (long long)g.N * g.modules * g.frames < 1024) return false;
   TcParams p; fill_common(p, g, e);
   p.BN = pick_bn(g.Cout, e.chunk);
+  static const int bn_override = getenv("CONVNET_B200_FPROP_BN") ? atoi(getenv("CONVNET_B200_FPROP_BN")) : 0;   // experiments
+  if (bn_override >= e.chunk && bn_override <= 256 && bn_override % e.chunk == 0 && !x_mode) p.BN = bn_override;
   p.kc_blocks = ceil_div(g.Cin, e.bk);
   p.x_mode = x_mode ? 1 : 0;
   p.x_yblocks = ceil_div(g.ky, 4);
@@ -940,8 +943,12 @@ static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float*
   p.st = st; p.so = so;
   p.bias = bias; p.relu = fuse.relu;
   p.idesc = ptx::make_idesc(bf ? 1 : 2, true, true, BM, p.BN);
-  apply_pair(p, kFprop, e.chunk, 1);
+  apply_pair(p, kFprop, 32, 1);
   const int bn_local = p.cta2 ? p.BN / 2 : p.BN;
+  // MN-major B is staged in whole chunks; a half tile that ends inside a chunk (bf16: BN = 192 -> 96 = 1.5 chunks) loads
+  // the rest of that chunk too (never read by the MMA) and cannot use the merged (o_lo, .., o_hi) view
+  p.b_rows = ceil_div(bn_local, e.chunk) * e.chunk;
+  if (p.cta2) p.b_tx_bytes = (uint32_t)p.b_rows * 128;
   CUtensorMap ma, mb;
   const long long img_off = (long long)g.cin0 * g.H * g.W * g.N;
   const void* img = images + img_off;
@@ -962,7 +969,7 @@ static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float*
   }
   if (p.splits > 1) { p.out = (float*)ws; p.bias = nullptr; p.relu = 0; }   // partial sums; the epilogue moves to reduce_split
   p.a_merged = (allow_merge() && g.frames == 1 && g.N % 128 == 0) ? 1 : 0;
-  p.b_merged = (allow_merge() && g.Cout % e.chunk == 0) ? 1 : 0;
+  p.b_merged = (allow_merge() && g.Cout % e.chunk == 0 && bn_local % e.chunk == 0) ? 1 : 0;
   // frames of a 3-D conv start in_frame_step floats apart and see Cin (= Cin3d*kt) channels
   if (x_mode) {
     const long long N = g.N;

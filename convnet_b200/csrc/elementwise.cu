@@ -149,11 +149,13 @@ __global__ void __launch_bounds__(256) softmax_kernel(float* x, int rows, int co
 }
 __global__ void softmax_ce_deriv_kernel(const float* __restrict__ p, const int* __restrict__ labels, float* deriv,
                                         float* loss, int rows, int cols) {
+  // blockIdx.y walks the classes: one thread per (image, class slice) instead of one per image (1 block for batch 128)
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= rows) return;
   const int lab = labels[n];
-  for (int c = 0; c < cols; c++) deriv[n + (long long)rows * c] = p[n + (long long)rows * c] - (c == lab ? 1.f : 0.f);
-  if (loss) loss[n] = -logf(fmaxf(p[n + (long long)rows * lab], 1e-30f));
+  for (int c = blockIdx.y; c < cols; c += gridDim.y)
+    deriv[n + (long long)rows * c] = p[n + (long long)rows * c] - (c == lab ? 1.f : 0.f);
+  if (loss && blockIdx.y == 0) loss[n] = -logf(fmaxf(p[n + (long long)rows * lab], 1e-30f));
 }
 __global__ void sum_kernel(const float* __restrict__ a, float* out, int n) {   // single block
   float s = 0.f;
@@ -221,7 +223,8 @@ void cnb_softmax(float* x, int rows, int cols) {
 }
 void cnb_softmax_ce_deriv(const float* probs, const int* labels, float* deriv, float* loss_per_image, int rows, int cols) {
   if (rows <= 0) return;
-  softmax_ce_deriv_kernel<<<ceil_div(rows, 128), 128, 0, state().stream>>>(probs, labels, deriv, loss_per_image, rows, cols);
+  const dim3 grid(ceil_div(rows, 128), std::max(1, std::min(cols, 4 * num_sms() / std::max(1, ceil_div(rows, 128)))));
+  softmax_ce_deriv_kernel<<<grid, 128, 0, state().stream>>>(probs, labels, deriv, loss_per_image, rows, cols);
   count_launch(); CNB_LAUNCH_CHECK("softmax_ce_deriv");
 }
 void cnb_sum(const float* a, float* out, int n) {

@@ -174,7 +174,10 @@ __global__ void __launch_bounds__(256) pool_undo_kernel(PoolGeom g, const float*
     for (int v = 0; v < VEC; v++) acc[v] += st * old[v];
     if (relu_mask) {                           // fused ApplyDerivativeOfActivation of the layer receiving this derivative
       float mk[VEC];
-      vload<VEC>(relu_mask + idx * VEC, mk);
+      if (MAX && relu_mask == images) {        // max-pool right above the ReLU layer: the mask is the pool input itself
+#pragma unroll
+        for (int v = 0; v < VEC; v++) mk[v] = img[v];
+      } else vload<VEC>(relu_mask + idx * VEC, mk);
 #pragma unroll
       for (int v = 0; v < VEC; v++) acc[v] = mk[v] > 0.f ? acc[v] : 0.f;
     }
@@ -196,7 +199,7 @@ static void launch_fwd(const PoolGeom& g, const float* images, float* targets, f
   cudaStream_t s = state().stream;
   const int planes = g.C * g.modT;
   const long long per_plane = total / planes;
-  CNB_REQUIRE(per_plane < (1LL << 31) && planes <= 65535, "pool_forward: plane too large");
+  CNB_REQUIRE(per_plane < (1LL << 30) && planes <= 65535, "pool_forward: plane too large");
   const dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(ceil_div<long long>(per_plane, 256), 64)), planes);
   const int k = (g.kt == 1 && g.T == 1 && g.modT == 1) ? std::max(g.kx, g.ky) : 99;
   if (k <= 2) pool_fwd_kernel<VEC, MAX, 2><<<grid, 256, 0, s>>>(g, images, targets, so, total);
@@ -225,7 +228,7 @@ static void launch_undo(const PoolGeom& g, const float* images, const float* gra
   cudaStream_t s = state().stream;
   const int planes = g.C * g.T;
   const long long per_plane = total / planes;
-  CNB_REQUIRE(per_plane < (1LL << 31) && planes <= 65535, "pool_undo: plane too large");
+  CNB_REQUIRE(per_plane < (1LL << 30) && planes <= 65535, "pool_undo: plane too large");
   const dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(ceil_div<long long>(per_plane, 256), 64)), planes);
   // windows covering one element per axis: ceil(k / stride)
   const int q = (g.kt == 1 && g.T == 1 && g.modT == 1) ? std::max(ceil_div(g.kx, g.sx), ceil_div(g.ky, g.sy)) : 99;
