@@ -185,6 +185,145 @@ __global__ void __launch_bounds__(256) pool_undo_kernel(PoolGeom g, const float*
   }
 }
 
+
+// ---- 2-D fast paths: one output ROW per block iteration ---------------------------------------------
+// The flat-index kernels above spend ~300-400 instructions per 16-byte result on index arithmetic (ncu: issue-bound at
+// 75 % issue slots, 2.8 TB/s).  Here everything that depends on the row (window rows, row base pointers) is computed
+// once per block iteration from blockIdx (uniform), the stride is a template constant (S = 0: run time), the image
+// index is a shift when N/VEC is a power of two, and per-thread offsets are 32-bit.
+template <int S> __device__ __forceinline__ int div_s(int a, int s) { return S > 0 ? a / S : a / s; }
+template <int S>
+__device__ __forceinline__ void cover_s(int X, int s, int p, int k, int mods, int& lo, int& hi) {
+  const int a = X - p - k + 1;
+  lo = a <= 0 ? 0 : div_s<S>(a + (S > 0 ? S : s) - 1, s);
+  const int b = X - p;
+  hi = b < 0 ? -1 : min(div_s<S>(b, s), mods - 1);
+}
+
+template <int VEC, bool MAX, int K, int S>
+__global__ void __launch_bounds__(256) pool_fwd_rows_kernel(PoolGeom g, const float* __restrict__ images,
+                                                             float* __restrict__ targets, float so, int nv_shift) {
+  const unsigned NV = g.N / VEC;
+  const unsigned rowlen = NV * g.modX;
+  const int sx = S > 0 ? S : g.sx, sy = S > 0 ? S : g.sy;
+  const float* img = images + (long long)g.N * g.W * g.H * blockIdx.y;        // this channel's input plane
+  float* out = targets + (long long)g.N * g.modX * g.modY * blockIdx.y;
+  for (int my = blockIdx.x; my < g.modY; my += gridDim.x) {
+    const int Y0 = my * sy + g.py;
+    for (unsigned t = threadIdx.x; t < rowlen; t += blockDim.x) {
+      const unsigned mx = nv_shift >= 0 ? (t >> nv_shift) : t / NV;
+      const unsigned nv = t - mx * NV;
+      const int X0 = (int)mx * sx + g.px;
+      float acc[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; v++) acc[v] = MAX ? -2e38f : 0.f;             // base value: gemm.cu:71
+      float a[K * K][VEC];
+      bool ok[K * K];
+#pragma unroll
+      for (int dy = 0; dy < K; dy++)
+#pragma unroll
+        for (int dx = 0; dx < K; dx++) {
+          const int X = X0 + dx, Y = Y0 + dy;
+          ok[dy * K + dx] = dy < g.ky && dx < g.kx && (unsigned)X < (unsigned)g.W && (unsigned)Y < (unsigned)g.H;
+          if (ok[dy * K + dx]) vload<VEC>(img + (unsigned)((Y * g.W + X) * g.N) + nv * VEC, a[dy * K + dx]);
+        }
+      int region = 0;
+#pragma unroll
+      for (int q = 0; q < K * K; q++)
+        if (ok[q]) {
+          region++;
+#pragma unroll
+          for (int v = 0; v < VEC; v++) acc[v] = MAX ? fmaxf(acc[v], a[q][v]) : acc[v] + a[q][v];
+        }
+      if (!MAX) {
+#pragma unroll
+        for (int v = 0; v < VEC; v++) acc[v] = acc[v] / region;             // CLIPPED count: gemm.cu:185
+      }
+#pragma unroll
+      for (int v = 0; v < VEC; v++) acc[v] = so * acc[v];
+      vstore<VEC>(out + (unsigned)(my * rowlen + t) * VEC, acc);
+    }
+  }
+}
+
+template <int VEC, bool MAX, int Q, int S>
+__global__ void __launch_bounds__(256) pool_undo_rows_kernel(PoolGeom g, const float* __restrict__ images,
+                                                              const float* __restrict__ grads,
+                                                              const float* __restrict__ acts, float* targets,
+                                                              float st, float so, const float* __restrict__ relu_mask,
+                                                              int nv_shift) {
+  const unsigned NV = g.N / VEC;
+  const unsigned rowlen = NV * g.W;
+  const long long in_plane = (long long)g.N * g.W * g.H * blockIdx.y, out_plane = (long long)g.N * g.modX * g.modY * blockIdx.y;
+  const float* img = MAX ? images + in_plane : nullptr;
+  const float* gr_p = grads + out_plane;
+  const float* ac_p = MAX ? acts + out_plane : nullptr;
+  const float* mk_p = relu_mask ? relu_mask + in_plane : nullptr;
+  const bool mask_is_input = MAX && relu_mask == images;     // max-pool right above the ReLU layer: mask == pool input
+  float* out = targets + in_plane;
+  for (int Y = blockIdx.x; Y < g.H; Y += gridDim.x) {
+    int y0, y1;
+    cover_s<S>(Y, g.sy, g.py, g.ky, g.modY, y0, y1);
+    for (unsigned t = threadIdx.x; t < rowlen; t += blockDim.x) {
+      const unsigned X = nv_shift >= 0 ? (t >> nv_shift) : t / NV;
+      const unsigned nv = t - X * NV;
+      const unsigned idx = (unsigned)(Y * rowlen + t) * VEC;
+      int x0, x1;
+      cover_s<S>((int)X, g.sx, g.px, g.kx, g.modX, x0, x1);
+      float im[VEC], acc[VEC], old[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; v++) { acc[v] = 0.f; old[v] = 0.f; im[v] = 0.f; }
+      if (MAX) vload<VEC>(img + idx, im);
+      if (st != 0.f) vload<VEC>(out + idx, old);
+      float gr[Q * Q][VEC], a[Q * Q][VEC];
+      bool ok[Q * Q];
+#pragma unroll
+      for (int j = 0; j < Q; j++)
+#pragma unroll
+        for (int i = 0; i < Q; i++) {
+          const int mx = x0 + i, my = y0 + j;
+          ok[j * Q + i] = mx <= x1 && my <= y1;
+          if (ok[j * Q + i]) {
+            const unsigned off = (unsigned)((my * g.modX + mx) * g.N) + nv * VEC;
+            vload<VEC>(gr_p + off, gr[j * Q + i]);
+            if (MAX) vload<VEC>(ac_p + off, a[j * Q + i]);
+          }
+        }
+#pragma unroll
+      for (int j = 0; j < Q; j++)
+#pragma unroll
+        for (int i = 0; i < Q; i++)
+          if (ok[j * Q + i]) {
+            if (MAX) {
+#pragma unroll
+              for (int v = 0; v < VEC; v++) acc[v] += (im[v] == a[j * Q + i][v]) ? so * gr[j * Q + i][v] : 0.f;   // ties duplicate: gemm.cu:291
+            } else {
+              int sX = (x0 + i) * g.sx + g.px, sY = (y0 + j) * g.sy + g.py;
+              const int eX = min(sX + g.kx, g.W), eY = min(sY + g.ky, g.H);
+              sX = max(sX, 0); sY = max(sY, 0);
+              const int region = (eX - sX) * (eY - sY);
+#pragma unroll
+              for (int v = 0; v < VEC; v++) acc[v] += so * gr[j * Q + i][v] / region;                            // gemm.cu:237
+            }
+          }
+#pragma unroll
+      for (int v = 0; v < VEC; v++) acc[v] += st * old[v];
+      if (relu_mask) {                         // fused ApplyDerivativeOfActivation of the layer receiving this derivative
+        float mk[VEC];
+        if (mask_is_input) {
+#pragma unroll
+          for (int v = 0; v < VEC; v++) mk[v] = im[v];
+        } else vload<VEC>(mk_p + idx, mk);
+#pragma unroll
+        for (int v = 0; v < VEC; v++) acc[v] = mk[v] > 0.f ? acc[v] : 0.f;
+      }
+      vstore<VEC>(out + idx, acc);
+    }
+  }
+}
+
+static int pow2_shift(unsigned v) { int s = 0; while ((1u << s) < v) s++; return (1u << s) == v ? s : -1; }
+
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 static int grid_for(long long total) {
@@ -202,6 +341,17 @@ static void launch_fwd(const PoolGeom& g, const float* images, float* targets, f
   CNB_REQUIRE(per_plane < (1LL << 30) && planes <= 65535, "pool_forward: plane too large");
   const dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(ceil_div<long long>(per_plane, 256), 64)), planes);
   const int k = (g.kt == 1 && g.T == 1 && g.modT == 1) ? std::max(g.kx, g.ky) : 99;
+  const long long in_plane = (long long)g.N * g.W * g.H;
+  if (k <= 3 && in_plane < (1LL << 31)) {          // 2-D, small window: the row-structured kernels
+    const dim3 rgrid((unsigned)g.modY, planes);
+    const int sh = pow2_shift(g.N / VEC);
+    const int S = (g.sx == g.sy && g.sx <= 2) ? g.sx : 0;
+#define CNB_POOL_FWD(KK, SS) pool_fwd_rows_kernel<VEC, MAX, KK, SS><<<rgrid, 256, 0, s>>>(g, images, targets, so, sh)
+    if (k <= 2) { if (S == 1) CNB_POOL_FWD(2, 1); else if (S == 2) CNB_POOL_FWD(2, 2); else CNB_POOL_FWD(2, 0); }
+    else { if (S == 1) CNB_POOL_FWD(3, 1); else if (S == 2) CNB_POOL_FWD(3, 2); else CNB_POOL_FWD(3, 0); }
+#undef CNB_POOL_FWD
+    return;
+  }
   if (k <= 2) pool_fwd_kernel<VEC, MAX, 2><<<grid, 256, 0, s>>>(g, images, targets, so, total);
   else if (k == 3) pool_fwd_kernel<VEC, MAX, 3><<<grid, 256, 0, s>>>(g, images, targets, so, total);
   else if (k == 4) pool_fwd_kernel<VEC, MAX, 4><<<grid, 256, 0, s>>>(g, images, targets, so, total);
@@ -232,6 +382,16 @@ static void launch_undo(const PoolGeom& g, const float* images, const float* gra
   const dim3 grid((unsigned)std::max<long long>(1, std::min<long long>(ceil_div<long long>(per_plane, 256), 64)), planes);
   // windows covering one element per axis: ceil(k / stride)
   const int q = (g.kt == 1 && g.T == 1 && g.modT == 1) ? std::max(ceil_div(g.kx, g.sx), ceil_div(g.ky, g.sy)) : 99;
+  if (q <= 2 && per_plane * VEC < (1LL << 31)) {   // 2-D, at most 2 x 2 covering windows: the row-structured kernels
+    const dim3 rgrid((unsigned)g.H, planes);
+    const int sh = pow2_shift(g.N / VEC);
+    const int S = (g.sx == g.sy && g.sx <= 2) ? g.sx : 0;
+#define CNB_POOL_UNDO(QQ, SS) pool_undo_rows_kernel<VEC, MAX, QQ, SS><<<rgrid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, mask, sh)
+    if (q <= 1) { if (S == 1) CNB_POOL_UNDO(1, 1); else if (S == 2) CNB_POOL_UNDO(1, 2); else CNB_POOL_UNDO(1, 0); }
+    else { if (S == 1) CNB_POOL_UNDO(2, 1); else if (S == 2) CNB_POOL_UNDO(2, 2); else CNB_POOL_UNDO(2, 0); }
+#undef CNB_POOL_UNDO
+    return;
+  }
   if (q <= 1) pool_undo_kernel<VEC, MAX, 1><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total, mask);
   else if (q == 2) pool_undo_kernel<VEC, MAX, 2><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total, mask);
   else pool_undo_kernel<VEC, MAX, 0><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total, mask);
