@@ -155,8 +155,14 @@ def conv_roofline(torch, lib, peaks, peak_kind, iters=10):
     flops = 2.0 * N * W * W * Cout * k * k * Cin
     achieved = flops / (ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops"]
+    traffic = None                          # DRAM bytes per launch from the committed ncu --set full capture of this kernel
+    if path == "tcgen05-bf16":
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_conv4_fprop_bf16_ncu.json")))["traffic_bytes_per_launch"]
+        except Exception:
+            traffic = None
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": None, "kernel": "tc_conv_kernel<fprop> (%s)" % path,
+            "traffic": traffic, "kernel": "tc_conv_kernel<fprop> (%s)" % path,
             "shape": "conv4 fprop 3x3 s1 p1, 14x14x768 -> 384, batch 256 (266.3 GFLOP)", "ms_per_launch": ms,
             "unstaged_call": {"ms": ms_call, "tflops": flops / (ms_call * 1e-3) / 1e12,
                               "note": "same conv call with the fp32 -> bf16 staging passes of both operands inside it"},
