@@ -70,6 +70,7 @@ void convnet_b200_set_stream(void* cuda_stream) { state().stream = (cudaStream_t
 void* convnet_b200_get_stream(void) { return (void*)state().stream; }
 void convnet_b200_set_conv_precision(int mode) {
   CNB_REQUIRE(mode >= 0 && mode <= 2, "convnet_b200_set_conv_precision");
+  if (mode != state().precision) bf16_invalidate(nullptr);      // staged copies do not survive a mode change
   state().precision = mode;
 }
 int convnet_b200_get_conv_precision(void) { return state().precision; }

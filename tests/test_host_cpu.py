@@ -92,3 +92,35 @@ def test_bench_reference_arm_non_root_ranks_exit_quietly():
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2"],
                        env=env, capture_output=True, text=True, timeout=120)
     assert r.returncode == 0 and r.stdout.strip() == ""
+
+
+def test_cpu_reference_sample_fits_its_time_budget(monkeypatch):
+    """bench.py's CPU arm sizes its sample per box: from a calibration run of the smallest layer set it picks the largest
+    set predicted to fit the budget (a 128-core box needed 274 s for the full step, an 8-core one 15 s)."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import cpu_reference as cr
+
+    class FakePool(cr.Pool):
+        def __init__(self, sec_per_gflop):              # no worker processes
+            self.cores, self.kind, self.sec_per_gflop, self.rate, self.ran = 8, "port", None, sec_per_gflop, []
+
+        def _run(self, layers, images_per_core=1):
+            self.ran.append(layers)
+            t = self.rate * cr.flops_per_image(layers) / 1e9 * images_per_core
+            return t, t
+
+    full = cr.flops_per_image(None)
+    assert abs(full / 1e9 - 11.87) < 0.01                                   # BASELINE.md 2c
+    fast = FakePool(sec_per_gflop=1.3)                                      # ~15 s for the full step
+    v, desc = fast.step(budget_s=25.0)
+    assert fast.ran == [cr.SAMPLES[0], None] and "all 14 weighted edges" in desc
+    assert abs(v - 8 / (1.3 * full / 1e9)) < 1e-9
+    slow = FakePool(sec_per_gflop=23.0)                                     # the 128-process box: 274 s for the full step
+    v, desc = slow.step(budget_s=25.0)
+    assert slow.ran[-1] == cr.SAMPLES[0] or slow.ran[-1] == cr.SAMPLES[1]
+    assert "extrapolated by FLOPs" in desc
+    assert slow.rate * cr.flops_per_image(slow.ran[-1]) / 1e9 <= 25.0 or slow.ran[-1] == cr.SAMPLES[0]
+    # extrapolation keeps images/s consistent with the calibrated rate
+    assert abs(v - 8 / (23.0 * full / 1e9)) / v < 1e-6
+    slow.step(budget_s=2.0)                                                 # calibration happens once
+    assert slow.ran.count(cr.SAMPLES[0]) >= 1 and len(slow.ran) == 3
