@@ -326,9 +326,6 @@ static int pow2_shift(unsigned v) { int s = 0; while ((1u << s) < v) s++; return
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-static int grid_for(long long total) {
-  static int mult = 0;
-  if (!mult) { const char* e = getenv("CONVNET_B200_POOL_GRID_MULT"); mult = e ? atoi(e) : 16; if (mult < 1) mult = 16; }
   const long long want = ceil_div<long long>(total, 256);
   return (int)std::min<long long>(want, (long long)num_sms() * mult);   // multiple of the SM count when large
 }
