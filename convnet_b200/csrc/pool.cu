@@ -326,10 +326,6 @@ static int pow2_shift(unsigned v) { int s = 0; while ((1u << s) < v) s++; return
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
-  const long long want = ceil_div<long long>(total, 256);
-  return (int)std::min<long long>(want, (long long)num_sms() * mult);   // multiple of the SM count when large
-}
-
 template <int VEC, bool MAX>
 static void launch_fwd(const PoolGeom& g, const float* images, float* targets, float so, long long total) {
   cudaStream_t s = state().stream;
