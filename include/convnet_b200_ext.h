@@ -42,7 +42,7 @@ int convnet_b200_last_conv_path(void);
 unsigned long long convnet_b200_launch_count(void);
 void convnet_b200_reset_launch_count(void);
 
-/* Free cached device scratch (wgrad partial sums).  Never required. */
+/* Free cached device scratch (wgrad / split-K partial sums, bf16 staging buffers).  Never required. */
 void convnet_b200_release_workspace(void);
 
 /* One-shot epilogue fusion for the NEXT conv / pool-undo call of this library (cleared by that call):
