@@ -298,6 +298,17 @@ def main():
     sampler.window(t0, time.time())                          # both timed regions run the same step under load
     clocks = sampler.stop() if rank == 0 else None
 
+    # replicas must still be in lock-step after the timed loops: a 64-bit checksum of the raw parameter bits, compared
+    # across ranks (the all-reduce result is identical on every rank, so every replica applied the same update)
+    p_bits = net.params_tensor().view(torch.int32).to(torch.int64)
+    checksum = (p_bits * (torch.arange(p_bits.numel(), device="cuda", dtype=torch.int64) % 8191 + 1)).sum().reshape(1)
+    replicas_identical = True
+    if world > 1:
+        sums = [torch.zeros_like(checksum) for _ in range(world)]
+        dist.all_gather(sums, checksum)
+        replicas_identical = all(int(t.item()) == int(sums[0].item()) for t in sums)
+        assert replicas_identical, "parameters diverged across ranks: %s" % [int(t.item()) for t in sums]
+
     images = args.batch * world * args.steps
     value = images / (ms_total * 1e-3)
     e2e_value = images / (ms_e2e * 1e-3)
@@ -325,6 +336,7 @@ def main():
             "model_tflops": value * net.flops_train / args.batch / 1e12,
             "roofline": roof,
             "last_loss": losses[-1] if losses else None,
+            "param_checksum": int(checksum.item()), "replicas_identical": replicas_identical,
         }
         if world == 1 and not args.no_cpu_baseline:
             import cpu_reference

@@ -17,8 +17,10 @@ LIB = os.path.join(LIBDIR, "libconvnet_b200.so")
 SOURCES = ["abi.cu", "ext.cu", "conv_simt.cu", "conv_tc.cu", "pool.cu", "rnorm.cu", "elementwise.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo",
-         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--use_fast_math",
+         "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden",
          "-ccbin", "g++"]
+# no --use_fast_math: softmax / cross-entropy / avg-pool division / the fp32 conv path are IEEE-compliant; the kernels
+# that want the fast intrinsics call them by name (rnorm: __powf, like the reference's --use_fast_math build)
 
 
 def _stamp():

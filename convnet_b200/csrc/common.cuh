@@ -59,7 +59,7 @@ struct Fuse {
 
 struct State {
   cudaStream_t stream = 0;          // legacy default stream, like every reference kernel
-  int precision = kPrecTF32;
+  int precision = kPrecFP32;      // the raw C ABI computes in fp32 (the reference's arithmetic) until a caller opts into tf32 / bf16
   int last_conv_path = kPathNone;
   unsigned long long launches = 0;  // kernels launched by this library
   // scratch (wgrad partial sums, rnorm-free) — grown on demand, never per-call malloc'd
@@ -75,6 +75,7 @@ State& state();
 
 void* workspace(size_t bytes);       // device scratch of at least `bytes`, valid until next call
 int num_sms();
+inline int current_device() { int d = 0; CNB_CUDA_CHECK(cudaGetDevice(&d)); return d; }
 
 inline void count_launch(int n = 1) { state().launches += n; }
 inline Fuse take_fuse() { Fuse f = state().fuse; state().fuse = Fuse(); return f; }

@@ -671,11 +671,13 @@ void launch(const CUtensorMap& a, const CUtensorMap& b, TcParams& p) {
   p.stages = pick_stages(p.b_rows);
   p.tmem_cols = tmem_cols_for(p.BN);
   const size_t smem = smem_bytes_for(p.b_rows, p.stages);
-  static bool attr_set = false;
-  if (!attr_set) {
+  // the attribute belongs to the (function, device) pair: set it once per device this process launches on
+  static unsigned long long attr_devices = 0;
+  const int dev = current_device();
+  if (dev >= 64 || !((attr_devices >> dev) & 1ULL)) {
     CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<OP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_conv_kernel<OP, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
+    if (dev < 64) attr_devices |= 1ULL << dev;
   }
   if (p.cta2) {
     // one cluster of two CTAs (one TPC) per scheduling unit; persistent over the pair tiles
@@ -807,13 +809,14 @@ void to_bf16(const float* src, __nv_bfloat16* dst, long long n) {
 inline size_t align_up(size_t v) { return (v + 1023) & ~size_t(1023); }
 
 // staged bf16 copies (convnet_b200_bf16_stage): a small table keyed by the fp32 tensor's base pointer
-struct Staged { const float* src; long long n; __nv_bfloat16* buf; size_t cap; bool valid; unsigned long long tick; };
+struct Staged { const float* src; long long n; __nv_bfloat16* buf; size_t cap; bool valid; unsigned long long tick; int dev; };
 std::vector<Staged>& staged_table() { static std::vector<Staged> t; return t; }
 unsigned long long g_stage_tick = 0;
 constexpr size_t kMaxStaged = 96;
 const __nv_bfloat16* staged(const float* src, long long n) {          // nullptr: not staged (or too short)
+  const int dev = current_device();
   for (Staged& e : staged_table())
-    if (e.valid && e.src == src && e.n >= n) { e.tick = ++g_stage_tick; return e.buf; }
+    if (e.valid && e.src == src && e.dev == dev && e.n >= n) { e.tick = ++g_stage_tick; return e.buf; }
   return nullptr;
 }
 
@@ -872,31 +875,43 @@ void bf16_invalidate(const float* ptr) {
 void bf16_release() {
   if (staged_table().empty()) return;
   CNB_CUDA_CHECK(cudaStreamSynchronize(state().stream));
-  for (Staged& e : staged_table()) if (e.buf) CNB_CUDA_CHECK(cudaFree(e.buf));
+  const int dev = current_device();
+  for (Staged& e : staged_table())
+    if (e.buf) {
+      if (e.dev != dev) CNB_CUDA_CHECK(cudaSetDevice(e.dev));
+      CNB_CUDA_CHECK(cudaFree(e.buf));
+      if (e.dev != dev) CNB_CUDA_CHECK(cudaSetDevice(dev));
+    }
   staged_table().clear();
 }
 void bf16_stage(const float* ptr, long long n) {
   if (!want_bf16() || ptr == nullptr || n <= 0 || !aligned16(ptr)) return;
   std::vector<Staged>& t = staged_table();
   Staged* slot = nullptr;
-  for (Staged& e : t) if (e.src == ptr) { slot = &e; break; }
+  const int dev = current_device();
+  for (Staged& e : t) if (e.src == ptr && e.dev == dev) { slot = &e; break; }
   if (!slot) {
     if (t.size() >= kMaxStaged) {                                       // recycle the least recently used entry
       slot = &t[0];
       for (Staged& e : t) if (e.tick < slot->tick) slot = &e;
     } else {
-      t.push_back(Staged{ptr, 0, nullptr, 0, false, 0});
+      t.push_back(Staged{ptr, 0, nullptr, 0, false, 0, dev});
       slot = &t.back();
     }
   }
   const size_t bytes = align_up((size_t)n * 2);
-  if (slot->cap < bytes) {
-    if (slot->buf) { CNB_CUDA_CHECK(cudaStreamSynchronize(state().stream)); CNB_CUDA_CHECK(cudaFree(slot->buf)); }
+  if (slot->cap < bytes || slot->dev != dev) {                          // (a recycled entry may belong to another device)
+    if (slot->buf) {
+      CNB_CUDA_CHECK(cudaStreamSynchronize(state().stream));
+      if (slot->dev != dev) CNB_CUDA_CHECK(cudaSetDevice(slot->dev));
+      CNB_CUDA_CHECK(cudaFree(slot->buf));
+      if (slot->dev != dev) CNB_CUDA_CHECK(cudaSetDevice(dev));
+    }
     slot->buf = nullptr; slot->cap = 0;
     CNB_CUDA_CHECK(cudaMalloc((void**)&slot->buf, bytes));
     slot->cap = bytes;
   }
-  slot->src = ptr; slot->n = n; slot->tick = ++g_stage_tick;
+  slot->src = ptr; slot->n = n; slot->dev = dev; slot->tick = ++g_stage_tick;
   to_bf16(ptr, slot->buf, n);
   slot->valid = true;
 }

@@ -50,16 +50,29 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Wait with a watchdog: a protocol bug must trap, not hang the GPU box.
+// Wait with a watchdog: a protocol bug must trap, not hang the GPU box.  The budget is WALL-CLOCK time (%globaltimer,
+// 20 s): a healthy wait that is merely descheduled (time slicing with another process, compute-sanitizer, ncu replay)
+// cannot reach it, and a dead pipeline still ends long before gpurun's own limit.  -DCNB_NO_MBAR_WATCHDOG removes it.
+__device__ __forceinline__ unsigned long long globaltimer_ns() {
+  unsigned long long t; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t)); return t;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+#ifdef CNB_NO_MBAR_WATCHDOG
+  while (!mbar_try_wait(bar, parity)) {}
+#else
+  unsigned long long t0 = 0;
+  unsigned spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {       // ~2 s at 2 GHz
+    if ((++spins & 0x3FFu) != 0) continue;                 // look at the clock every 1024 failed polls only
+    const unsigned long long now = globaltimer_ns();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 20000000000ULL) {
       printf("convnet_b200: mbarrier wait timed out (block %d thread %d)\n", blockIdx.x, threadIdx.x);
       __trap();
     }
   }
+#endif
 }
 
 // ---- TMA tiled loads (global -> shared, completes on an mbarrier) ------------------------------

@@ -57,9 +57,11 @@ void Layer::ApplyDerivativeOfActivation() {
   if (deriv_fused_) return;
   if (config_.activation == RECTIFIED_LINEAR) deriv_.ApplyDerivOfReLU(state_);
 }
-void Layer::ApplyDropout(bool train, unsigned long long step) {      // layer.cc:367-395, scale-up at train time
+void Layer::ApplyDropout(bool train, unsigned long long step, unsigned long long salt) {      // layer.cc:367-395, scale-up at train time
   if (config_.dropprob <= 0 || !train) return;
-  const unsigned long long seed = (std::hash<std::string>()(config_.name) ^ (step * 0x9E3779B97F4A7C15ULL));
+  // salt = model seed and data-parallel rank (the reference seeds each process with seed + rank, convnet.cc:67-68):
+  // replicas must not draw the same mask for the same local image index
+  const unsigned long long seed = (std::hash<std::string>()(config_.name) ^ (step * 0x9E3779B97F4A7C15ULL)) ^ salt;
   cnb_dropout(state_.GetDevData(), dropout_mask_.GetDevData(), (long long)state_.GetNumEls(), config_.dropprob,
               1.0f / (1.0f - config_.dropprob), seed);
 }
@@ -253,7 +255,7 @@ void ConvNet::Fprop(bool train) {                            // convnet.cc:377-3
     Edge* e = edges_[i - 1];
     e->ComputeUp(layers_[i - 1]->GetState(), l->GetState(), /*overwrite=*/true, train);
     l->ApplyActivation();
-    l->ApplyDropout(train, step_);
+    l->ApplyDropout(train, step_, dropout_salt_);
   }
 }
 
@@ -320,6 +322,8 @@ std::vector<Bucket> PlanBuckets(const std::vector<size_t>& edge_offset, const st
 
 void ConvNet::SetDataParallel(DataParallelSync* dp, size_t bucket_floats) {
   dp_ = dp;
+  dropout_salt_ = ((unsigned long long)model_.seed * 0xA24BAED4963EE407ULL) ^
+                  ((unsigned long long)((dp ? dp->rank() : 0) + 1) * 0xD1B54A32D192ED03ULL);
   buckets_ = PlanBuckets(edge_offset_, edge_size_, bucket_floats);
 }
 void ConvNet::BroadcastParameters() {

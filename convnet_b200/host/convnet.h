@@ -41,7 +41,7 @@ class Layer {                                   // src/layer.{h,cc}, reduced to 
   void AllocateMemory(int batch_size);
   void ApplyActivation();                       // layer.cc:545-560
   void ApplyDerivativeOfActivation();           // layer.cc:562-580
-  void ApplyDropout(bool train, unsigned long long step);   // layer.cc:  mask = rand > dropprob ; state *= mask
+  void ApplyDropout(bool train, unsigned long long step, unsigned long long salt);   // layer.cc:  mask = rand > dropprob ; state *= mask
   void ApplyDerivativeofDropout();
   void ComputeDeriv();                          // softmax + cross-entropy: deriv = p - onehot   (loss_functions.cc)
   Matrix& GetState() { return state_; }
@@ -138,6 +138,7 @@ class ConvNet {
   DataParallelSync* dp_ = nullptr;
   std::vector<Bucket> buckets_;
   unsigned long long step_ = 0;
+  unsigned long long dropout_salt_ = 0xD1B54A32D192ED03ULL;      // model seed and data-parallel rank, see SetDataParallel
 };
 
 // src/grad_check.{h,cc}: finite-difference check of dLoss/dparam for the first k weights and biases
