@@ -15,12 +15,28 @@ namespace {
 ConvDesc as_2d(ConvDesc d) { d.kernel_size_t = 1; d.stride_t = 1; d.padding_t = 0; return d; }
 
 // ---- dispatch: tensor-core path when the mode and the shape allow, else fp32 CUDA cores
+// Writer protocol (stage.cu): drop staged bf16 copies overlapping the target; when the caller asked for a fresh copy
+// (convnet_b200_emit_bf16_next) hand the kernel the buffer, and convert in a trailing pass if the kernel did not fill it.
+struct Emit {
+  float* target; long long n; __nv_bfloat16* buf = nullptr; bool done = false;
+  Emit(float* t, long long n_, bool want) : target(t), n(n_) {
+    bf16_note_write(t, n_);
+    if (want) buf = bf16_emit_slot(t, n_);          // nullptr outside bf16 mode; marked valid: the kernel below fills it
+  }
+  void attach(Fuse& f) { f.out16 = buf; f.emitted = &done; }
+  void finish() { if (buf && !done) bf16_stage(target, n); }     // nobody filled it: one conversion pass (re-validates the slot)
+};
+
 void conv_up(const ConvGeom& g, const float* images, const float* filters, float* targets, float st, float so) {
   Fuse fuse = take_fuse();
   if (!g.conv && fuse.any()) { fprintf(stderr, "convnet_b200: epilogue fusion is not available for untied filters\n"); abort(); }
-  if (state().precision != kPrecFP32 && tc_conv_up(g, images, filters, targets, st, so, fuse)) return;
-  simt_conv_up(g, images, filters, targets, st, so, fuse);
-  state().last_conv_path = kPathSimt;
+  Emit emit(targets, g.out_total, fuse.emit_bf16 != 0);
+  emit.attach(fuse);
+  if (!(state().precision != kPrecFP32 && tc_conv_up(g, images, filters, targets, st, so, fuse))) {
+    simt_conv_up(g, images, filters, targets, st, so, fuse);
+    state().last_conv_path = kPathSimt;
+  }
+  emit.finish();
 }
 
 void conv_down(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float st, float so) {
@@ -29,11 +45,17 @@ void conv_down(const ConvGeom& g, const float* derivs, const float* filters, flo
   const bool whole = g.conv && g.frames == 1 && g.cin0 == 0 && g.Cin == g.CinT;
   const float* late_mask = nullptr;
   if (fuse.relu_mask && !whole) { late_mask = fuse.relu_mask; fuse.relu_mask = nullptr; }
+  Emit emit(targets, g.img_total, fuse.emit_bf16 != 0);
+  if (!late_mask) emit.attach(fuse);               // a late mask changes the values after the kernel: convert afterwards
   if (!(state().precision != kPrecFP32 && tc_conv_down(g, derivs, filters, targets, st, so, fuse))) {
     simt_conv_down(g, derivs, filters, targets, st, so, fuse);
     state().last_conv_path = kPathSimt;
   }
-  if (late_mask) cnb_relu_deriv(targets, late_mask, g.img_total);
+  if (late_mask) {
+    const long long n4 = g.img_total;             // (cnb_relu_deriv would consume a pending fuse request; none is pending here)
+    cnb_relu_deriv(targets, late_mask, n4);
+  }
+  emit.finish();
 }
 
 // reduction split for the CUDA-core wgrad: enough (tile x chunk) blocks to fill the GPU
@@ -49,6 +71,7 @@ void simt_outp_auto(const ConvGeom& g, const float* images, const float* derivs,
 }
 
 void conv_outp(const ConvGeom& g, const float* images, const float* derivs, float* targets, float st, float so) {
+  take_fuse();                                 // a wgrad call has no epilogue to fuse: a pending request must not leak to a later call
   if (!g.conv) {                               // untied: one [Cout x K] block per module
     simt_conv_outp(g, images, derivs, targets, 1, 1, true, st, so);
     state().last_conv_path = kPathSimt;
@@ -78,7 +101,10 @@ void do_conv_outp(const char* what, cudamat* images, cudamat* derivs, cudamat* t
 void do_pool(const char* what, bool is_max, cudamat* images, cudamat* targets, Shape4D* is, Shape4D* ts, ConvDesc d,
              float so) {
   PoolGeom g = pool_geom(*is, *ts, images, targets, d, what);
-  pool_forward(g, is_max, images->data_device, targets->data_device, so);
+  const Fuse fuse = take_fuse();
+  Emit emit(targets->data_device, (long long)targets->size[0] * targets->size[1], fuse.emit_bf16 != 0);
+  emit.done = pool_forward(g, is_max, images->data_device, targets->data_device, so, emit.buf);
+  emit.finish();
 }
 void do_max_undo(const char* what, cudamat* images, cudamat* maxGrads, cudamat* maxActs, cudamat* targets,
                  Shape4D* is, Shape4D* gs, ConvDesc d, float st) {
@@ -86,14 +112,18 @@ void do_max_undo(const char* what, cudamat* images, cudamat* maxGrads, cudamat* 
   CNB_REQUIRE(targets->size[0] == g.N && targets->size[1] == images->size[1], what);
   CNB_REQUIRE(maxActs->size[0] == g.N && maxActs->size[1] == maxGrads->size[1], what);
   const Fuse fuse = take_fuse();
-  max_pool_undo(g, images->data_device, maxGrads->data_device, maxActs->data_device, targets->data_device, st, 1.f,
-                fuse.relu_mask);
+  Emit emit(targets->data_device, (long long)targets->size[0] * targets->size[1], fuse.emit_bf16 != 0);
+  emit.done = max_pool_undo(g, images->data_device, maxGrads->data_device, maxActs->data_device, targets->data_device, st,
+                            1.f, fuse.relu_mask, emit.buf);
+  emit.finish();
 }
 void do_avg_undo(const char* what, cudamat* avgGrads, cudamat* targets, Shape4D* gs, Shape4D* ts, ConvDesc d, float st,
                  float so) {
   PoolGeom g = pool_geom(*ts, *gs, targets, avgGrads, d, what);
   const Fuse fuse = take_fuse();
-  avg_pool_undo(g, avgGrads->data_device, targets->data_device, st, so, fuse.relu_mask);
+  Emit emit(targets->data_device, (long long)targets->size[0] * targets->size[1], fuse.emit_bf16 != 0);
+  emit.done = avg_pool_undo(g, avgGrads->data_device, targets->data_device, st, so, fuse.relu_mask, emit.buf);
+  emit.finish();
 }
 
 ConvDesc sample_desc(Shape4D* is, Shape4D* ts, int factor) {      // gemm.cu:1503-1541
@@ -115,9 +145,17 @@ void do_rnorm(const char* what, cudamat* images, cudamat* targets, int F, int si
   CNB_REQUIRE(els % ((long long)F * frames) == 0, what);
   CNB_REQUIRE(targets->size[0] == images->size[0] && targets->size[1] == images->size[1], what);
   const long long L = els / F / frames;          // locations per frame
+  // fused epilogue (convnet_b200_fuse_next relu / convnet_b200_emit_bf16_next): in the tile kernel when it applies, else
+  // as trailing passes
+  const Fuse fuse = take_fuse();
+  const bool fusable = rnorm_can_fuse(F);
+  Emit emit(targets->data_device, els, fuse.emit_bf16 != 0);
   for (int t = 0; t < frames; t++)               // conv3d_gemm.cu:167-189: independent per frame
     rnorm_forward(images->data_device + (long long)t * L * F, targets->data_device + (long long)t * L * F, L, F, sizeF,
-                  a, b, blocked);
+                  a, b, blocked, fusable && fuse.relu, fusable && emit.buf ? emit.buf + (long long)t * L * F : nullptr);
+  if (fuse.relu && !fusable) cnb_relu(targets->data_device, els);
+  emit.done = fusable;
+  emit.finish();
 }
 void do_rnorm_undo(const char* what, cudamat* outGrads, cudamat* inputs, cudamat* targets, int F, int sizeF, float a,
                    float b, bool blocked, int frames) {
@@ -127,9 +165,12 @@ void do_rnorm_undo(const char* what, cudamat* outGrads, cudamat* inputs, cudamat
   CNB_REQUIRE(targets->size[0] == inputs->size[0] && targets->size[1] == inputs->size[1], what);
   CNB_REQUIRE(outGrads->size[0] == inputs->size[0] && outGrads->size[1] == inputs->size[1], what);
   const long long L = els / F / frames;
+  const Fuse fuse = take_fuse();
+  Emit emit(targets->data_device, els, fuse.emit_bf16 != 0);
   for (int t = 0; t < frames; t++)
     rnorm_undo(outGrads->data_device + (long long)t * L * F, inputs->data_device + (long long)t * L * F,
                targets->data_device + (long long)t * L * F, L, F, sizeF, a, b, blocked);
+  emit.finish();
 }
 
 }  // namespace
@@ -207,6 +248,7 @@ void ResponseNormCrossMapRpropGemm(cudamat*, cudamat*, cudamat*, int, int, float
   not_implemented("ResponseNormCrossMapRpropGemm", "R-operator has no caller in the reference's C++; out of scope");
 }
 void Scale(cudamat* mat, float scale) {
+  bf16_note_write(mat->data_device, (long long)mat->size[0] * mat->size[1]);
   scale_buffer(mat->data_device, (long long)mat->size[0] * mat->size[1], scale);
 }
 

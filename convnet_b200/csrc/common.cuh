@@ -1,5 +1,6 @@
 // common.cuh — library-wide state and helpers (sm_100a only).
 #pragma once
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
@@ -54,6 +55,10 @@ struct Fuse {
   const float* bias = nullptr;       // fprop: + bias[output channel]
   int relu = 0;                      // fprop: max(., 0) after the bias
   const float* relu_mask = nullptr;  // dgrad / pool undo: result zeroed where relu_mask <= 0 (same shape as the target)
+  int emit_bf16 = 0;                 // any writer: also leave a staged bf16 copy of the whole target (convnet_b200_emit_bf16_next)
+  // internal (filled by the ABI wrapper): where the bf16 twin of the target goes; a kernel that writes it sets *emitted
+  __nv_bfloat16* out16 = nullptr;
+  bool* emitted = nullptr;
   bool any() const { return bias || relu || relu_mask; }
 };
 

@@ -1,5 +1,7 @@
 // conv_kernels.h — host-side entry points of the kernel translation units.
 #pragma once
+#include <cuda_bf16.h>
+
 #include "common.cuh"
 #include "geom.h"
 
@@ -24,21 +26,37 @@ bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, 
 bool tc_conv_outp(const ConvGeom& g, const float* images, const float* derivs, float* targets,
                   float scaleTargets, float scaleOutput);
 
-// bf16 operand staging (convnet_b200_bf16_stage / _invalidate); release drops the buffers too
-void bf16_stage(const float* ptr, long long n);
+// stage.cu — bf16 operand copies and their coherence (convnet_b200_bf16_stage / _ensure / _invalidate / emit)
+bool want_bf16();
+void to_bf16(const float* src, __nv_bfloat16* dst, long long n);
+const __nv_bfloat16* bf16_staged(const float* src, long long n);      // valid copy covering [src, src+n), or nullptr
+void bf16_stage(const float* ptr, long long n);                        // convert now
+void bf16_ensure(const float* ptr, long long n);                       // convert unless a valid copy exists
 void bf16_invalidate(const float* ptr);
-void bf16_release();
+void bf16_note_write(const float* ptr, long long n);                   // [ptr, ptr+n) is being overwritten: overlapping copies go stale
+__nv_bfloat16* bf16_emit_slot(const float* ptr, long long n);          // buffer a producing kernel fills itself (marked valid)
+__nv_bfloat16* bf16_refresh_slot(const float* ptr, long long n);       // the existing buffer of exactly this tensor, or nullptr
+void bf16_release();                                                   // drops the buffers too
+// writer protocol: begin_write drops stale copies and returns the buffer the kernel must fill when it can emit; end_write
+// falls back to a conversion pass when emission was wanted but the kernel could not do it
+__nv_bfloat16* begin_write(float* target, long long n, bool want_emit, bool kernel_can_emit);
+void end_write(float* target, long long n, bool want_emit, const __nv_bfloat16* emitted);
 
 // pool.cu
-void pool_forward(const PoolGeom& g, bool is_max, const float* images, float* targets, float scaleOutput);
-void max_pool_undo(const PoolGeom& g, const float* images, const float* maxGrads, const float* maxActs,
-                   float* targets, float scaleTargets, float scaleOutput, const float* relu_mask);
-void avg_pool_undo(const PoolGeom& g, const float* avgGrads, float* targets, float scaleTargets,
-                   float scaleOutput, const float* relu_mask);
+// targets_bf16 (may be null): also write the bf16 twin of the target; the return value says whether the kernel did
+bool pool_forward(const PoolGeom& g, bool is_max, const float* images, float* targets, float scaleOutput,
+                  __nv_bfloat16* targets_bf16 = nullptr);
+bool max_pool_undo(const PoolGeom& g, const float* images, const float* maxGrads, const float* maxActs,
+                   float* targets, float scaleTargets, float scaleOutput, const float* relu_mask,
+                   __nv_bfloat16* targets_bf16 = nullptr);
+bool avg_pool_undo(const PoolGeom& g, const float* avgGrads, float* targets, float scaleTargets,
+                   float scaleOutput, const float* relu_mask, __nv_bfloat16* targets_bf16 = nullptr);
 
 // rnorm.cu
+// relu / targets_bf16: fused epilogue (max(., 0); a bf16 copy of the output) — only when rnorm_can_fuse(numFilters)
 void rnorm_forward(const float* images, float* targets, long long num_locs, int numFilters, int sizeF,
-                   float addScale, float powScale, bool blocked);
+                   float addScale, float powScale, bool blocked, bool relu = false, __nv_bfloat16* targets_bf16 = nullptr);
+bool rnorm_can_fuse(int numFilters);
 void rnorm_undo(const float* outGrads, const float* inputs, float* targets, long long num_locs,
                 int numFilters, int sizeF, float addScale, float powScale, bool blocked);
 

@@ -782,43 +782,7 @@ bool merged_image_map(CUtensorMap* m, const void* base, const Elem& e, const Con
   return make_map(m, base, e, 5, dims, str, box, true);
 }
 
-// ---- bf16 staging: one HBM-bound pass fp32 -> bf16 (round to nearest even) per operand -------------
-__global__ void __launch_bounds__(256) cvt_bf16_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n) {
-  const long long n8 = n >> 3;
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += stride) {
-    const float4 a = __ldg(reinterpret_cast<const float4*>(src) + 2 * i), b = __ldg(reinterpret_cast<const float4*>(src) + 2 * i + 1);
-    __nv_bfloat162 r0 = __floats2bfloat162_rn(a.x, a.y), r1 = __floats2bfloat162_rn(a.z, a.w);
-    __nv_bfloat162 r2 = __floats2bfloat162_rn(b.x, b.y), r3 = __floats2bfloat162_rn(b.z, b.w);
-    uint4 o;
-    o.x = *reinterpret_cast<uint32_t*>(&r0); o.y = *reinterpret_cast<uint32_t*>(&r1);
-    o.z = *reinterpret_cast<uint32_t*>(&r2); o.w = *reinterpret_cast<uint32_t*>(&r3);
-    reinterpret_cast<uint4*>(dst)[i] = o;
-  }
-  if (blockIdx.x == 0 && threadIdx.x < (n & 7)) dst[(n8 << 3) + threadIdx.x] = __float2bfloat16_rn(src[(n8 << 3) + threadIdx.x]);
-}
-void to_bf16(const float* src, __nv_bfloat16* dst, long long n) {
-  static const int dbg = getenv("CONVNET_B200_TC_DEBUG") ? atoi(getenv("CONVNET_B200_TC_DEBUG")) : 0;
-  if (dbg & 4) return;
-  const long long n8 = n >> 3;
-  const int grid = (int)std::min<long long>(std::max<long long>(ceil_div<long long>(n8, 256), 1), 8LL * num_sms());
-  cvt_bf16_kernel<<<grid, 256, 0, state().stream>>>(src, dst, n);
-  count_launch();
-  CNB_LAUNCH_CHECK("cvt_bf16");
-}
 inline size_t align_up(size_t v) { return (v + 1023) & ~size_t(1023); }
-
-// staged bf16 copies (convnet_b200_bf16_stage): a small table keyed by the fp32 tensor's base pointer
-struct Staged { const float* src; long long n; __nv_bfloat16* buf; size_t cap; bool valid; unsigned long long tick; int dev; };
-std::vector<Staged>& staged_table() { static std::vector<Staged> t; return t; }
-unsigned long long g_stage_tick = 0;
-constexpr size_t kMaxStaged = 96;
-const __nv_bfloat16* staged(const float* src, long long n) {          // nullptr: not staged (or too short)
-  const int dev = current_device();
-  for (Staged& e : staged_table())
-    if (e.valid && e.src == src && e.dev == dev && e.n >= n) { e.tick = ++g_stage_tick; return e.buf; }
-  return nullptr;
-}
 
 // ---- split-K for 1x1 / FC shapes: too few output tiles to fill the GPU, long K ------------------------
 // out = st*out + so * sum_s part[s]  (+ bias[channel], ReLU | zero where mask <= 0): the fused epilogue moves here
@@ -863,58 +827,9 @@ int pick_ksplit(const TcParams& p, const ConvGeom& g, long long out_elems) {
   const int want = std::min(num_sms() / p.num_tiles, p.kc_blocks / 4);
   return std::max(want, 1);
 }
-bool want_bf16() { return state().precision == kPrecBF16; }
 inline bool aligned16(const void* q) { return (reinterpret_cast<uintptr_t>(q) & 15) == 0; }
 
 }  // namespace
-
-void bf16_invalidate(const float* ptr) {
-  for (Staged& e : staged_table())
-    if (ptr == nullptr || e.src == ptr) e.valid = false;
-}
-void bf16_release() {
-  if (staged_table().empty()) return;
-  CNB_CUDA_CHECK(cudaStreamSynchronize(state().stream));
-  const int dev = current_device();
-  for (Staged& e : staged_table())
-    if (e.buf) {
-      if (e.dev != dev) CNB_CUDA_CHECK(cudaSetDevice(e.dev));
-      CNB_CUDA_CHECK(cudaFree(e.buf));
-      if (e.dev != dev) CNB_CUDA_CHECK(cudaSetDevice(dev));
-    }
-  staged_table().clear();
-}
-void bf16_stage(const float* ptr, long long n) {
-  if (!want_bf16() || ptr == nullptr || n <= 0 || !aligned16(ptr)) return;
-  std::vector<Staged>& t = staged_table();
-  Staged* slot = nullptr;
-  const int dev = current_device();
-  for (Staged& e : t) if (e.src == ptr && e.dev == dev) { slot = &e; break; }
-  if (!slot) {
-    if (t.size() >= kMaxStaged) {                                       // recycle the least recently used entry
-      slot = &t[0];
-      for (Staged& e : t) if (e.tick < slot->tick) slot = &e;
-    } else {
-      t.push_back(Staged{ptr, 0, nullptr, 0, false, 0, dev});
-      slot = &t.back();
-    }
-  }
-  const size_t bytes = align_up((size_t)n * 2);
-  if (slot->cap < bytes || slot->dev != dev) {                          // (a recycled entry may belong to another device)
-    if (slot->buf) {
-      CNB_CUDA_CHECK(cudaStreamSynchronize(state().stream));
-      if (slot->dev != dev) CNB_CUDA_CHECK(cudaSetDevice(slot->dev));
-      CNB_CUDA_CHECK(cudaFree(slot->buf));
-      if (slot->dev != dev) CNB_CUDA_CHECK(cudaSetDevice(dev));
-    }
-    slot->buf = nullptr; slot->cap = 0;
-    CNB_CUDA_CHECK(cudaMalloc((void**)&slot->buf, bytes));
-    slot->cap = bytes;
-  }
-  slot->src = ptr; slot->n = n; slot->dev = dev; slot->tick = ++g_stage_tick;
-  to_bf16(ptr, slot->buf, n);
-  slot->valid = true;
-}
 
 // ---- fprop ---------------------------------------------------------------------------------------
 // `bf` selects bf16 operands (CONVNET_B200_PRECISION=bf16): images and filters are first rounded to bf16 copies in
@@ -971,8 +886,8 @@ static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float*
   const long long taps = (long long)g.kx * g.ky;
   uint8_t* ws = nullptr;
   if (bf) {
-    const __nv_bfloat16* si = staged(images, g.img_total);
-    const __nv_bfloat16* sf = staged(filters, (long long)g.Cout * g.K);
+    const __nv_bfloat16* si = bf16_staged(images, g.img_total);
+    const __nv_bfloat16* sf = bf16_staged(filters, (long long)g.Cout * g.K);
     const size_t ib = si ? 0 : align_up((size_t)g.img_total * 2), fb = sf ? 0 : align_up((size_t)g.Cout * g.K * 2);
     if (part_bytes + ib + fb) ws = (uint8_t*)workspace(part_bytes + ib + fb);
     if (!si) { to_bf16(images, (__nv_bfloat16*)(ws + part_bytes), g.img_total); si = (const __nv_bfloat16*)(ws + part_bytes); }
@@ -1072,8 +987,8 @@ static bool tc_conv_down_impl(const ConvGeom& g, const float* derivs, const floa
   const void* flt = filters;
   uint8_t* ws = nullptr;
   if (bf) {
-    const __nv_bfloat16* sd = staged(derivs, g.out_total);
-    const __nv_bfloat16* sf = staged(filters, (long long)g.Cout * g.K);
+    const __nv_bfloat16* sd = bf16_staged(derivs, g.out_total);
+    const __nv_bfloat16* sf = bf16_staged(filters, (long long)g.Cout * g.K);
     const size_t db = sd ? 0 : align_up((size_t)g.out_total * 2), fb = sf ? 0 : align_up((size_t)g.Cout * g.K * 2);
     if (part_bytes + db + fb) ws = (uint8_t*)workspace(part_bytes + db + fb);
     if (!sd) { to_bf16(derivs, (__nv_bfloat16*)(ws + part_bytes), g.out_total); sd = (const __nv_bfloat16*)(ws + part_bytes); }
@@ -1163,8 +1078,8 @@ static bool tc_conv_outp_impl(const ConvGeom& g, const float* images, const floa
   const size_t part_bytes = p.splits > 1 ? align_up(sizeof(float) * elems * p.splits) : 0;
   uint8_t* ws = nullptr;
   if (bf) {
-    const __nv_bfloat16* si = staged(images, g.img_total);
-    const __nv_bfloat16* sd = staged(derivs, g.out_total);
+    const __nv_bfloat16* si = bf16_staged(images, g.img_total);
+    const __nv_bfloat16* sd = bf16_staged(derivs, g.out_total);
     const size_t ib = si ? 0 : align_up((size_t)g.img_total * 2), db = sd ? 0 : align_up((size_t)g.out_total * 2);
     if (part_bytes + ib + db) ws = (uint8_t*)workspace(part_bytes + ib + db);
     if (!si) { to_bf16(images, (__nv_bfloat16*)(ws + part_bytes), g.img_total); si = (const __nv_bfloat16*)(ws + part_bytes); }

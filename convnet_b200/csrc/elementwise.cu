@@ -3,10 +3,20 @@
 // call sites they correspond to.  All are single-pass, float4-vectorised where aligned.
 #include <algorithm>
 
+#include <cuda_bf16.h>
+
 #include "../../include/convnet_b200_ext.h"
-#include "common.cuh"
+#include "conv_kernels.h"
 
 namespace cnb {
+
+// optional bf16 twin of a float4 result (convnet_b200_emit_bf16_next): 8 more bytes per thread, no extra pass
+__device__ __forceinline__ void emit4(__nv_bfloat16* out16, long long i4, const float4& v) {
+  if (!out16) return;
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v.x, v.y), hi = __floats2bfloat162_rn(v.z, v.w);
+  uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+  reinterpret_cast<uint2*>(out16)[i4] = o;
+}
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 static int blocks_for(long long work, int threads) {
@@ -74,14 +84,15 @@ __global__ void colsum_final_kernel(const float* __restrict__ part, float* out, 
 }
 
 // n4 = number of float4 groups (vector body); the scalar tail [4*n4, n) is handled by the same launch
-__global__ void relu_kernel(float* x, long long n, long long n4) {
+__global__ void relu_kernel(float* x, long long n, long long n4, __nv_bfloat16* out16) {
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
   for (long long i = tid; i < n4; i += nt) {
     float4 v = reinterpret_cast<float4*>(x)[i];
     v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f);
     reinterpret_cast<float4*>(x)[i] = v;
+    emit4(out16, i, v);
   }
-  for (long long i = 4 * n4 + tid; i < n; i += nt) x[i] = fmaxf(x[i], 0.f);
+  for (long long i = 4 * n4 + tid; i < n; i += nt) { const float v = fmaxf(x[i], 0.f); x[i] = v; if (out16) out16[i] = __float2bfloat16_rn(v); }
 }
 __global__ void relu_deriv_kernel(float* dx, const float* __restrict__ y, long long n, long long n4) {
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
@@ -93,12 +104,46 @@ __global__ void relu_deriv_kernel(float* dx, const float* __restrict__ y, long l
   }
   for (long long i = 4 * n4 + tid; i < n; i += nt) dx[i] = y[i] > 0.f ? dx[i] : 0.f;
 }
-__global__ void sgd_kernel(float* w, float* h, const float* __restrict__ g, long long n, float lr, float mom, float l2) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float wi = w[i];
-    const float hi = mom * h[i] + lr * (g[i] + l2 * wi);
-    h[i] = hi;
-    w[i] = wi - hi;
+// Multi-tensor SGD with momentum and L2 decay: ONE launch updates every tensor of a batch (an all-reduce bucket, or the
+// whole net).  A block owns kSgdChunk consecutive elements of one tensor; the block -> tensor map is a prefix table that
+// travels in the kernel parameters (no device-side descriptor to keep coherent).  Tensors whose staged bf16 copy exists
+// (conv weights in bf16 mode) get it refreshed from the same registers.
+constexpr int kSgdMaxTensors = 48, kSgdChunk = 4096;
+struct SgdItem { float* w; float* h; const float* g; __nv_bfloat16* w16; long long n; float lr, mom, l2; int vec; };
+struct SgdBatch { int count; int first_block[kSgdMaxTensors + 1]; SgdItem t[kSgdMaxTensors]; };
+
+__global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ SgdBatch b) {
+  int ti = 0;
+  while (ti + 1 < b.count && (int)blockIdx.x >= b.first_block[ti + 1]) ti++;      // <= 48 uniform steps
+  const SgdItem& t = b.t[ti];
+  const long long e0 = (long long)((int)blockIdx.x - b.first_block[ti]) * kSgdChunk;
+  const long long e1 = min(t.n, e0 + kSgdChunk);
+  if (t.vec) {                                                                     // all pointers 16-byte aligned
+    for (long long i = e0 + 4 * threadIdx.x; i < e1; i += 4 * 256) {
+      if (i + 4 <= e1) {
+        float4 w = *reinterpret_cast<const float4*>(t.w + i), h = *reinterpret_cast<const float4*>(t.h + i);
+        const float4 g = __ldg(reinterpret_cast<const float4*>(t.g + i));
+        h.x = t.mom * h.x + t.lr * (g.x + t.l2 * w.x); w.x -= h.x;
+        h.y = t.mom * h.y + t.lr * (g.y + t.l2 * w.y); w.y -= h.y;
+        h.z = t.mom * h.z + t.lr * (g.z + t.l2 * w.z); w.z -= h.z;
+        h.w = t.mom * h.w + t.lr * (g.w + t.l2 * w.w); w.w -= h.w;
+        *reinterpret_cast<float4*>(t.h + i) = h;
+        *reinterpret_cast<float4*>(t.w + i) = w;
+        emit4(t.w16, i >> 2, w);
+      } else {
+        for (long long j = i; j < e1; j++) {
+          const float wi = t.w[j], hi = t.mom * t.h[j] + t.lr * (t.g[j] + t.l2 * wi);
+          t.h[j] = hi; t.w[j] = wi - hi;
+          if (t.w16) t.w16[j] = __float2bfloat16_rn(wi - hi);
+        }
+      }
+    }
+  } else {
+    for (long long i = e0 + threadIdx.x; i < e1; i += 256) {
+      const float wi = t.w[i], hi = t.mom * t.h[i] + t.lr * (t.g[i] + t.l2 * wi);
+      t.h[i] = hi; t.w[i] = wi - hi;
+      if (t.w16) t.w16[i] = __float2bfloat16_rn(wi - hi);
+    }
   }
 }
 
@@ -106,23 +151,41 @@ __device__ __forceinline__ uint32_t hash_u32(unsigned long long x) {     // spli
   x += 0x9E3779B97F4A7C15ULL; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL; x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
   return (uint32_t)((x ^ (x >> 31)) >> 32);
 }
-__global__ void dropout_kernel(float* x, float* mask, long long n, float dropprob, float scale, unsigned long long seed) {
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+// n4 float4 groups (vector body) + scalar tail, like relu_kernel; element i always draws from hash(seed + i)
+__global__ void dropout_kernel(float* x, float* mask, long long n, long long n4, float dropprob, float scale,
+                               unsigned long long seed, __nv_bfloat16* out16) {
+  const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
+  for (long long i = tid; i < n4; i += nt) {
+    float4 v = reinterpret_cast<float4*>(x)[i], m;
+    const unsigned long long b = seed + 4ULL * (unsigned long long)i;
+    m.x = hash_u32(b) * (1.0f / 4294967296.0f) >= dropprob ? scale : 0.f;
+    m.y = hash_u32(b + 1) * (1.0f / 4294967296.0f) >= dropprob ? scale : 0.f;
+    m.z = hash_u32(b + 2) * (1.0f / 4294967296.0f) >= dropprob ? scale : 0.f;
+    m.w = hash_u32(b + 3) * (1.0f / 4294967296.0f) >= dropprob ? scale : 0.f;
+    v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
+    reinterpret_cast<float4*>(mask)[i] = m;
+    reinterpret_cast<float4*>(x)[i] = v;
+    emit4(out16, i, v);
+  }
+  for (long long i = 4 * n4 + tid; i < n; i += nt) {
     const float u = hash_u32(seed + (unsigned long long)i) * (1.0f / 4294967296.0f);
     const float m = u >= dropprob ? scale : 0.f;
     mask[i] = m;
-    x[i] *= m;
+    const float v = x[i] * m;
+    x[i] = v;
+    if (out16) out16[i] = __float2bfloat16_rn(v);
   }
 }
-__global__ void mult_kernel(float* a, const float* __restrict__ b, long long n, long long n4) {
+__global__ void mult_kernel(float* a, const float* __restrict__ b, long long n, long long n4, __nv_bfloat16* out16) {
   const long long tid = blockIdx.x * (long long)blockDim.x + threadIdx.x, nt = (long long)gridDim.x * blockDim.x;
   for (long long i = tid; i < n4; i += nt) {
     float4 x = reinterpret_cast<float4*>(a)[i];
     const float4 m = __ldg(reinterpret_cast<const float4*>(b) + i);
     x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
     reinterpret_cast<float4*>(a)[i] = x;
+    emit4(out16, i, x);
   }
-  for (long long i = 4 * n4 + tid; i < n; i += nt) a[i] *= b[i];
+  for (long long i = 4 * n4 + tid; i < n; i += nt) { const float v = a[i] * b[i]; a[i] = v; if (out16) out16[i] = __float2bfloat16_rn(v); }
 }
 
 // softmax over classes of a column-major [rows x cols] matrix: one block per 32 images; lane = image (coalesced
@@ -178,10 +241,16 @@ using namespace cnb;
 extern "C" {
 
 void cnb_add_channel_bias(float* acts, const float* bias, long long rows, int cols) {
+  const bool emit = take_fuse().emit_bf16 != 0;
+  begin_write(acts, rows * cols, emit, false);
   bias_launch<false>(acts, bias, rows, cols);
+  end_write(acts, rows * cols, emit, nullptr);
 }
 void cnb_add_channel_bias_relu(float* acts, const float* bias, long long rows, int cols) {
+  const bool emit = take_fuse().emit_bf16 != 0;
+  begin_write(acts, rows * cols, emit, false);
   bias_launch<true>(acts, bias, rows, cols);
+  end_write(acts, rows * cols, emit, nullptr);
 }
 void cnb_channel_bias_grad(const float* derivs, float* grad_bias, long long rows, int cols, float st, float so) {
   if (cols <= 0) return;
@@ -194,35 +263,51 @@ void cnb_channel_bias_grad(const float* derivs, float* grad_bias, long long rows
   CNB_LAUNCH_CHECK("channel_bias_grad");
 }
 void cnb_relu(float* x, long long n) {
+  const bool emit = take_fuse().emit_bf16 != 0;
   if (n <= 0) return;
   const long long n4 = aligned16(x) ? n / 4 : 0;
-  relu_kernel<<<blocks_for(std::max(n4, n - 4 * n4), 256), 256, 0, state().stream>>>(x, n, n4);
+  __nv_bfloat16* o16 = begin_write(x, n, emit, true);
+  relu_kernel<<<blocks_for(std::max(n4, n - 4 * n4), 256), 256, 0, state().stream>>>(x, n, n4, o16);
   count_launch(); CNB_LAUNCH_CHECK("relu");
+  end_write(x, n, emit, o16);
 }
 void cnb_relu_deriv(float* dx, const float* y, long long n) {
+  const bool emit = take_fuse().emit_bf16 != 0;
   if (n <= 0) return;
+  begin_write(dx, n, emit, false);
   const long long n4 = (aligned16(dx) && aligned16(y)) ? n / 4 : 0;
   relu_deriv_kernel<<<blocks_for(std::max(n4, n - 4 * n4), 256), 256, 0, state().stream>>>(dx, y, n, n4);
   count_launch(); CNB_LAUNCH_CHECK("relu_deriv");
+  end_write(dx, n, emit, nullptr);
 }
 void cnb_dropout(float* x, float* mask, long long n, float dropprob, float scale, unsigned long long seed) {
+  const bool emit = take_fuse().emit_bf16 != 0;
   if (n <= 0) return;
-  dropout_kernel<<<blocks_for(n, 256), 256, 0, state().stream>>>(x, mask, n, dropprob, scale, seed);
+  const long long n4 = (aligned16(x) && aligned16(mask)) ? n / 4 : 0;
+  __nv_bfloat16* o16 = begin_write(x, n, emit, true);
+  bf16_note_write(mask, n);
+  dropout_kernel<<<blocks_for(std::max(n4, n - 4 * n4), 256), 256, 0, state().stream>>>(x, mask, n, n4, dropprob, scale, seed, o16);
   count_launch(); CNB_LAUNCH_CHECK("dropout");
+  end_write(x, n, emit, o16);
 }
 void cnb_mult(float* a, const float* b, long long n) {
+  const bool emit = take_fuse().emit_bf16 != 0;
   if (n <= 0) return;
   const long long n4 = (aligned16(a) && aligned16(b)) ? n / 4 : 0;
-  mult_kernel<<<blocks_for(std::max(n4, n - 4 * n4), 256), 256, 0, state().stream>>>(a, b, n, n4);
+  __nv_bfloat16* o16 = begin_write(a, n, emit, true);
+  mult_kernel<<<blocks_for(std::max(n4, n - 4 * n4), 256), 256, 0, state().stream>>>(a, b, n, n4, o16);
   count_launch(); CNB_LAUNCH_CHECK("mult");
+  end_write(a, n, emit, o16);
 }
 void cnb_softmax(float* x, int rows, int cols) {
   if (rows <= 0) return;
+  bf16_note_write(x, (long long)rows * cols);
   softmax_kernel<<<ceil_div(rows, 32), 256, 0, state().stream>>>(x, rows, cols);
   count_launch(); CNB_LAUNCH_CHECK("softmax");
 }
 void cnb_softmax_ce_deriv(const float* probs, const int* labels, float* deriv, float* loss_per_image, int rows, int cols) {
   if (rows <= 0) return;
+  bf16_note_write(deriv, (long long)rows * cols);
   const dim3 grid(ceil_div(rows, 128), std::max(1, std::min(cols, 4 * num_sms() / std::max(1, ceil_div(rows, 128)))));
   softmax_ce_deriv_kernel<<<grid, 128, 0, state().stream>>>(probs, labels, deriv, loss_per_image, rows, cols);
   count_launch(); CNB_LAUNCH_CHECK("softmax_ce_deriv");
@@ -231,10 +316,33 @@ void cnb_sum(const float* a, float* out, int n) {
   sum_kernel<<<1, 256, 0, state().stream>>>(a, out, n);
   count_launch(); CNB_LAUNCH_CHECK("sum");
 }
+void cnb_sgd_momentum_multi(const CnbSgdTensor* tensors, int count) {
+  for (int base = 0; base < count; base += kSgdMaxTensors) {
+    SgdBatch b;
+    b.count = 0;
+    int blocks = 0;
+    for (int i = base; i < count && b.count < kSgdMaxTensors; i++) {
+      const CnbSgdTensor& s = tensors[i];
+      if (s.n <= 0) continue;
+      SgdItem& t = b.t[b.count];
+      t.w = s.w; t.h = s.hist; t.g = s.grad; t.n = s.n; t.lr = s.lr; t.mom = s.momentum; t.l2 = s.l2;
+      t.vec = (aligned16(s.w) && aligned16(s.hist) && aligned16(s.grad)) ? 1 : 0;
+      // the weights change: a staged bf16 copy of exactly this tensor is refreshed in the same pass, any other overlap dropped
+      t.w16 = bf16_refresh_slot(s.w, s.n);
+      if (!t.w16) bf16_note_write(s.w, s.n);
+      b.first_block[b.count] = blocks;
+      blocks += (int)ceil_div<long long>(s.n, kSgdChunk);
+      b.count++;
+    }
+    if (b.count == 0) continue;
+    b.first_block[b.count] = blocks;
+    sgd_multi_kernel<<<blocks, 256, 0, state().stream>>>(b);
+    count_launch(); CNB_LAUNCH_CHECK("sgd_momentum_multi");
+  }
+}
 void cnb_sgd_momentum(float* w, float* hist, const float* grad, long long n, float lr, float momentum, float l2) {
-  if (n <= 0) return;
-  sgd_kernel<<<blocks_for(n, 256), 256, 0, state().stream>>>(w, hist, grad, n, lr, momentum, l2);
-  count_launch(); CNB_LAUNCH_CHECK("sgd_momentum");
+  CnbSgdTensor t = {w, hist, grad, n, lr, momentum, l2};
+  cnb_sgd_momentum_multi(&t, 1);
 }
 
 }  // extern "C"

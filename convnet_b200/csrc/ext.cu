@@ -77,7 +77,10 @@ int convnet_b200_get_conv_precision(void) { return state().precision; }
 void convnet_b200_fuse_next(const float* bias, int relu, const float* relu_mask) {
   state().fuse.bias = bias; state().fuse.relu = relu; state().fuse.relu_mask = relu_mask;
 }
+void convnet_b200_emit_bf16_next(void) { state().fuse.emit_bf16 = 1; }
 void convnet_b200_bf16_stage(const float* ptr, long long n) { bf16_stage(ptr, n); }
+void convnet_b200_bf16_ensure(const float* ptr, long long n) { bf16_ensure(ptr, n); }
+int convnet_b200_bf16_is_staged(const float* ptr, long long n) { return want_bf16() && bf16_staged(ptr, n) != nullptr; }
 void convnet_b200_bf16_invalidate(const float* ptr) { bf16_invalidate(ptr); }
 int convnet_b200_last_conv_path(void) { return state().last_conv_path; }
 unsigned long long convnet_b200_launch_count(void) { return state().launches; }

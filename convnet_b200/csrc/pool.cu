@@ -7,6 +7,8 @@
 // fully coalesced 16-byte access.  Backward passes are GATHERS over the windows that
 // cover an input element: no atomics, deterministic (the reference scatters with
 // atomicAdd + __syncthreads per tap).
+#include <cuda_bf16.h>
+
 #include <algorithm>
 
 #include "conv_kernels.h"
@@ -27,6 +29,14 @@ template <> __device__ __forceinline__ void vstore<4>(float* p, const float (&v)
   *reinterpret_cast<float4*>(p) = make_float4(v[0], v[1], v[2], v[3]);
 }
 template <> __device__ __forceinline__ void vstore<1>(float* p, const float (&v)[1]) { *p = v[0]; }
+// optional bf16 twin of a result (convnet_b200_emit_bf16_next); p16 is indexed like the fp32 target
+template <int VEC> __device__ __forceinline__ void vemit(__nv_bfloat16* p16, const float (&v)[VEC]);
+template <> __device__ __forceinline__ void vemit<4>(__nv_bfloat16* p16, const float (&v)[4]) {
+  const __nv_bfloat162 lo = __floats2bfloat162_rn(v[0], v[1]), hi = __floats2bfloat162_rn(v[2], v[3]);
+  uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+  *reinterpret_cast<uint2*>(p16) = o;
+}
+template <> __device__ __forceinline__ void vemit<1>(__nv_bfloat16* p16, const float (&v)[1]) { *p16 = __float2bfloat16_rn(v[0]); }
 
 // ---- forward -------------------------------------------------------------------------
 // K > 0: 2-D window with kx, ky <= K, fully unrolled with predicated loads so that all K*K 16-byte loads of a
@@ -202,12 +212,14 @@ __device__ __forceinline__ void cover_s(int X, int s, int p, int k, int mods, in
 
 template <int VEC, bool MAX, int K, int S>
 __global__ void __launch_bounds__(256) pool_fwd_rows_kernel(PoolGeom g, const float* __restrict__ images,
-                                                             float* __restrict__ targets, float so, int nv_shift) {
+                                                             float* __restrict__ targets, float so, int nv_shift,
+                                                             __nv_bfloat16* __restrict__ targets16) {
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * g.modX;
   const int sx = S > 0 ? S : g.sx, sy = S > 0 ? S : g.sy;
   const float* img = images + (long long)g.N * g.W * g.H * blockIdx.y;        // this channel's input plane
   float* out = targets + (long long)g.N * g.modX * g.modY * blockIdx.y;
+  __nv_bfloat16* out16 = targets16 ? targets16 + (long long)g.N * g.modX * g.modY * blockIdx.y : nullptr;
   for (int my = blockIdx.x; my < g.modY; my += gridDim.x) {
     const int Y0 = my * sy + g.py;
     for (unsigned t = threadIdx.x; t < rowlen; t += blockDim.x) {
@@ -242,6 +254,7 @@ __global__ void __launch_bounds__(256) pool_fwd_rows_kernel(PoolGeom g, const fl
 #pragma unroll
       for (int v = 0; v < VEC; v++) acc[v] = so * acc[v];
       vstore<VEC>(out + (unsigned)(my * rowlen + t) * VEC, acc);
+      if (out16) vemit<VEC>(out16 + (unsigned)(my * rowlen + t) * VEC, acc);
     }
   }
 }
@@ -251,7 +264,7 @@ __global__ void __launch_bounds__(256) pool_undo_rows_kernel(PoolGeom g, const f
                                                               const float* __restrict__ grads,
                                                               const float* __restrict__ acts, float* targets,
                                                               float st, float so, const float* __restrict__ relu_mask,
-                                                              int nv_shift) {
+                                                              int nv_shift, __nv_bfloat16* __restrict__ targets16) {
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * g.W;
   const long long in_plane = (long long)g.N * g.W * g.H * blockIdx.y, out_plane = (long long)g.N * g.modX * g.modY * blockIdx.y;
@@ -261,6 +274,7 @@ __global__ void __launch_bounds__(256) pool_undo_rows_kernel(PoolGeom g, const f
   const float* mk_p = relu_mask ? relu_mask + in_plane : nullptr;
   const bool mask_is_input = MAX && relu_mask == images;     // max-pool right above the ReLU layer: mask == pool input
   float* out = targets + in_plane;
+  __nv_bfloat16* out16 = targets16 ? targets16 + in_plane : nullptr;
   for (int Y = blockIdx.x; Y < g.H; Y += gridDim.x) {
     int y0, y1;
     cover_s<S>(Y, g.sy, g.py, g.ky, g.modY, y0, y1);
@@ -318,6 +332,7 @@ __global__ void __launch_bounds__(256) pool_undo_rows_kernel(PoolGeom g, const f
         for (int v = 0; v < VEC; v++) acc[v] = mk[v] > 0.f ? acc[v] : 0.f;
       }
       vstore<VEC>(out + idx, acc);
+      if (out16) vemit<VEC>(out16 + idx, acc);
     }
   }
 }
@@ -327,7 +342,7 @@ static int pow2_shift(unsigned v) { int s = 0; while ((1u << s) < v) s++; return
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
 template <int VEC, bool MAX>
-static void launch_fwd(const PoolGeom& g, const float* images, float* targets, float so, long long total) {
+static bool launch_fwd(const PoolGeom& g, const float* images, float* targets, float so, long long total, __nv_bfloat16* t16) {
   cudaStream_t s = state().stream;
   const int planes = g.C * g.modT;
   const long long per_plane = total / planes;
@@ -339,35 +354,38 @@ static void launch_fwd(const PoolGeom& g, const float* images, float* targets, f
     const dim3 rgrid((unsigned)g.modY, planes);
     const int sh = pow2_shift(g.N / VEC);
     const int S = (g.sx == g.sy && g.sx <= 2) ? g.sx : 0;
-#define CNB_POOL_FWD(KK, SS) pool_fwd_rows_kernel<VEC, MAX, KK, SS><<<rgrid, 256, 0, s>>>(g, images, targets, so, sh)
+#define CNB_POOL_FWD(KK, SS) pool_fwd_rows_kernel<VEC, MAX, KK, SS><<<rgrid, 256, 0, s>>>(g, images, targets, so, sh, t16)
     if (k <= 2) { if (S == 1) CNB_POOL_FWD(2, 1); else if (S == 2) CNB_POOL_FWD(2, 2); else CNB_POOL_FWD(2, 0); }
     else { if (S == 1) CNB_POOL_FWD(3, 1); else if (S == 2) CNB_POOL_FWD(3, 2); else CNB_POOL_FWD(3, 0); }
 #undef CNB_POOL_FWD
-    return;
+    return t16 != nullptr;
   }
   if (k <= 2) pool_fwd_kernel<VEC, MAX, 2><<<grid, 256, 0, s>>>(g, images, targets, so, total);
   else if (k == 3) pool_fwd_kernel<VEC, MAX, 3><<<grid, 256, 0, s>>>(g, images, targets, so, total);
   else if (k == 4) pool_fwd_kernel<VEC, MAX, 4><<<grid, 256, 0, s>>>(g, images, targets, so, total);
   else pool_fwd_kernel<VEC, MAX, 0><<<grid, 256, 0, s>>>(g, images, targets, so, total);
+  return false;
 }
 
-void pool_forward(const PoolGeom& g, bool is_max, const float* images, float* targets, float so) {
+bool pool_forward(const PoolGeom& g, bool is_max, const float* images, float* targets, float so, __nv_bfloat16* targets_bf16) {
   const bool v4 = (g.N % 4 == 0) && aligned16(images) && aligned16(targets);
   const long long outs = (long long)g.modX * g.modY * g.C * g.modT;
+  bool emitted;
   if (v4) {
-    if (is_max) launch_fwd<4, true>(g, images, targets, so, outs * (g.N / 4));
-    else launch_fwd<4, false>(g, images, targets, so, outs * (g.N / 4));
+    if (is_max) emitted = launch_fwd<4, true>(g, images, targets, so, outs * (g.N / 4), targets_bf16);
+    else emitted = launch_fwd<4, false>(g, images, targets, so, outs * (g.N / 4), targets_bf16);
   } else {
-    if (is_max) launch_fwd<1, true>(g, images, targets, so, outs * g.N);
-    else launch_fwd<1, false>(g, images, targets, so, outs * g.N);
+    if (is_max) emitted = launch_fwd<1, true>(g, images, targets, so, outs * g.N, targets_bf16);
+    else emitted = launch_fwd<1, false>(g, images, targets, so, outs * g.N, targets_bf16);
   }
   count_launch();
   CNB_LAUNCH_CHECK("pool_forward");
+  return emitted;
 }
 
 template <int VEC, bool MAX>
-static void launch_undo(const PoolGeom& g, const float* images, const float* grads, const float* acts, float* targets,
-                        float st, float so, long long total, const float* mask) {
+static bool launch_undo(const PoolGeom& g, const float* images, const float* grads, const float* acts, float* targets,
+                        float st, float so, long long total, const float* mask, __nv_bfloat16* t16) {
   cudaStream_t s = state().stream;
   const int planes = g.C * g.T;
   const long long per_plane = total / planes;
@@ -379,40 +397,44 @@ static void launch_undo(const PoolGeom& g, const float* images, const float* gra
     const dim3 rgrid((unsigned)g.H, planes);
     const int sh = pow2_shift(g.N / VEC);
     const int S = (g.sx == g.sy && g.sx <= 2) ? g.sx : 0;
-#define CNB_POOL_UNDO(QQ, SS) pool_undo_rows_kernel<VEC, MAX, QQ, SS><<<rgrid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, mask, sh)
+#define CNB_POOL_UNDO(QQ, SS) pool_undo_rows_kernel<VEC, MAX, QQ, SS><<<rgrid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, mask, sh, t16)
     if (q <= 1) { if (S == 1) CNB_POOL_UNDO(1, 1); else if (S == 2) CNB_POOL_UNDO(1, 2); else CNB_POOL_UNDO(1, 0); }
     else { if (S == 1) CNB_POOL_UNDO(2, 1); else if (S == 2) CNB_POOL_UNDO(2, 2); else CNB_POOL_UNDO(2, 0); }
 #undef CNB_POOL_UNDO
-    return;
+    return t16 != nullptr;
   }
   if (q <= 1) pool_undo_kernel<VEC, MAX, 1><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total, mask);
   else if (q == 2) pool_undo_kernel<VEC, MAX, 2><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total, mask);
   else pool_undo_kernel<VEC, MAX, 0><<<grid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, total, mask);
+  return false;
 }
 
-static void undo(const PoolGeom& g, bool is_max, const float* images, const float* grads, const float* acts,
-                 float* targets, float st, float so, const float* mask) {
+static bool undo(const PoolGeom& g, bool is_max, const float* images, const float* grads, const float* acts,
+                 float* targets, float st, float so, const float* mask, __nv_bfloat16* t16) {
   const bool v4 = (g.N % 4 == 0) && aligned16(grads) && aligned16(targets) && (!mask || aligned16(mask)) &&
                   (!is_max || (aligned16(images) && aligned16(acts)));
   const long long ins = (long long)g.W * g.H * g.C * g.T;
+  bool emitted;
   if (v4) {
-    if (is_max) launch_undo<4, true>(g, images, grads, acts, targets, st, so, ins * (g.N / 4), mask);
-    else launch_undo<4, false>(g, images, grads, acts, targets, st, so, ins * (g.N / 4), mask);
+    if (is_max) emitted = launch_undo<4, true>(g, images, grads, acts, targets, st, so, ins * (g.N / 4), mask, t16);
+    else emitted = launch_undo<4, false>(g, images, grads, acts, targets, st, so, ins * (g.N / 4), mask, t16);
   } else {
-    if (is_max) launch_undo<1, true>(g, images, grads, acts, targets, st, so, ins * g.N, mask);
-    else launch_undo<1, false>(g, images, grads, acts, targets, st, so, ins * g.N, mask);
+    if (is_max) emitted = launch_undo<1, true>(g, images, grads, acts, targets, st, so, ins * g.N, mask, t16);
+    else emitted = launch_undo<1, false>(g, images, grads, acts, targets, st, so, ins * g.N, mask, t16);
   }
   count_launch();
   CNB_LAUNCH_CHECK("pool_undo");
+  return emitted;
 }
 
-void max_pool_undo(const PoolGeom& g, const float* images, const float* maxGrads, const float* maxActs,
-                   float* targets, float st, float so, const float* relu_mask) {
-  undo(g, true, images, maxGrads, maxActs, targets, st, so, relu_mask);
+bool max_pool_undo(const PoolGeom& g, const float* images, const float* maxGrads, const float* maxActs,
+                   float* targets, float st, float so, const float* relu_mask, __nv_bfloat16* targets_bf16) {
+  return undo(g, true, images, maxGrads, maxActs, targets, st, so, relu_mask, targets_bf16);
 }
 
-void avg_pool_undo(const PoolGeom& g, const float* avgGrads, float* targets, float st, float so, const float* relu_mask) {
-  undo(g, false, nullptr, avgGrads, nullptr, targets, st, so, relu_mask);
+bool avg_pool_undo(const PoolGeom& g, const float* avgGrads, float* targets, float st, float so, const float* relu_mask,
+                   __nv_bfloat16* targets_bf16) {
+  return undo(g, false, nullptr, avgGrads, nullptr, targets, st, so, relu_mask, targets_bf16);
 }
 
 }  // namespace cnb

@@ -17,6 +17,8 @@
 //   forward window of channel j : [j - a, j + b]  with a = k/2, b = k - k/2 - 1   (gemm.cu:475-477)
 //   inverse window of channel j : [j - b, j + a]                                 (gemm.cu:528-530)
 //   blocked: both are the block [ (j/k)*k, (j/k)*k + k ).
+#include <cuda_bf16.h>
+
 #include <algorithm>
 
 #include "conv_kernels.h"
@@ -222,6 +224,182 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_undo_kernel(const float* __r
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Tile kernels (the default whenever one tile fits in shared memory).
+//
+// The channel walk above is a serial dependency chain per location with its loads inside the chain: ncu showed the
+// backward pass issue/latency-bound at 0.30 of the HBM peak.  Here a CTA owns a tile of TL consecutive locations x ALL
+// channels and works in phases that are either fully parallel or touch shared memory only:
+//   1. the whole x (and dy) tile is fetched with 16-byte cp.async — every load of the tile is in flight at once;
+//   2. an exclusive prefix sum of x^2 along the channels is built in shared memory (a thread per (location, channel
+//      segment); two short passes: segment totals, then the running prefix offset by the earlier segments);
+//   3. every (channel, location) in parallel: S = Q[hi] - Q[lo] (the window sum as a prefix difference), base, one
+//      __powf, then y (forward) or t = dy x base^(-b-1) and p = dy base^(-b) (backward);
+//   4. backward only: exclusive prefix of t in place, then dx_j = p_j - 2ab x_j (R[hi'] - R[lo']) in parallel;
+//   5. results leave with 16-byte stores (optionally ReLU'd, optionally also as a bf16 copy for the next conv).
+// Windows (cudamat_conv_gemm.cu:475-477, 528-530): forward [i-a, i+b], inverse [j-b, j+a], a = k/2, b = k-a-1;
+// blocked: both are [(i/k)k, (i/k)k + k).  Prefix differences cost ~F/k ulps of relative error on S (<= 1e-6 here).
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void rn_cp16(float* smem_dst, const float* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void rn_cp_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+template <int TL>
+__device__ __forceinline__ void rn_load_tile(float* dst, const float* __restrict__ src, long long L, long long l0, int F,
+                                             int valid, bool vec) {
+  if (vec && valid == TL) {
+    constexpr int Q4 = TL / 4;
+    for (int idx = threadIdx.x; idx < F * Q4; idx += RN_THREADS) {
+      const int f = idx / Q4, c = idx - f * Q4;
+      rn_cp16(dst + f * TL + 4 * c, src + (long long)f * L + l0 + 4 * c);
+    }
+  } else {
+    for (int idx = threadIdx.x; idx < F * TL; idx += RN_THREADS) {
+      const int f = idx / TL, l = idx - f * TL;
+      dst[idx] = l < valid ? __ldg(src + (long long)f * L + l0 + l) : 0.f;
+    }
+  }
+}
+
+// exclusive prefix along channels of SQ ? v^2 : v, `src` -> `dst` (may alias), dst has F+1 rows; all 128 threads call it
+template <int TL, bool SQ>
+__device__ __forceinline__ void rn_prefix(const float* src, float* dst, float* segtot, int F) {
+  constexpr int NSEG = RN_THREADS / TL;
+  const int l = threadIdx.x % TL, s = threadIdx.x / TL;
+  const int fs = (F + NSEG - 1) / NSEG, f0 = min(F, s * fs), f1 = min(F, f0 + fs);
+  float tot = 0.f;
+  if (NSEG > 1) {
+    for (int f = f0; f < f1; f++) { const float v = src[f * TL + l]; tot += SQ ? v * v : v; }
+    segtot[s * TL + l] = tot;
+    __syncthreads();
+    tot = 0.f;
+    for (int q = 0; q < s; q++) tot += segtot[q * TL + l];
+  }
+  float run = tot;
+  for (int f = f0; f < f1; f++) { const float v = src[f * TL + l]; dst[f * TL + l] = run; run += SQ ? v * v : v; }
+  if (f1 == F && (s == NSEG - 1 || f0 < F)) dst[F * TL + l] = run;       // the segment that ends at F writes the total
+  __syncthreads();
+}
+
+__device__ __forceinline__ void rn_window(int i, int F, int k, int a, int b, bool blocked, int& lo, int& hi) {
+  if (blocked) { lo = (i / k) * k; hi = min(F, lo + k); }
+  else { lo = max(0, i - a); hi = min(F, i + b + 1); }
+}
+
+__device__ __forceinline__ void rn_store4(float* __restrict__ out, __nv_bfloat16* __restrict__ out16, long long off, float4 r,
+                                          int l, int valid, bool vec) {
+  if (vec && valid >= l + 4) {
+    *reinterpret_cast<float4*>(out + off) = r;
+    if (out16) {
+      const __nv_bfloat162 lo = __floats2bfloat162_rn(r.x, r.y), hi = __floats2bfloat162_rn(r.z, r.w);
+      uint2 o; o.x = *reinterpret_cast<const uint32_t*>(&lo); o.y = *reinterpret_cast<const uint32_t*>(&hi);
+      *reinterpret_cast<uint2*>(out16 + off) = o;
+    }
+  } else {
+    const float rv[4] = {r.x, r.y, r.z, r.w};
+    for (int v = 0; v < 4; v++)
+      if (l + v < valid) { out[off + v] = rv[v]; if (out16) out16[off + v] = __float2bfloat16_rn(rv[v]); }
+  }
+}
+
+template <int TL>
+__global__ void __launch_bounds__(RN_THREADS) rnorm_fwd_tile_kernel(const float* __restrict__ x, float* __restrict__ y,
+                                                                     __nv_bfloat16* __restrict__ y16, long long L, int F,
+                                                                     int k, float alpha, float beta, int blocked, int relu,
+                                                                     int vec) {
+  extern __shared__ __align__(16) float sm[];
+  float* X = sm;                               // [F][TL]
+  float* Q = X + (size_t)F * TL;               // [F+1][TL] exclusive prefix of x^2
+  float* segtot = Q + (size_t)(F + 1) * TL;    // [128/TL][TL]
+  const long long l0 = (long long)blockIdx.x * TL;
+  const int valid = (int)min((long long)TL, L - l0);
+  rn_load_tile<TL>(X, x, L, l0, F, valid, vec != 0);
+  rn_cp_wait_all();
+  __syncthreads();
+  rn_prefix<TL, true>(X, Q, segtot, F);
+  const int a = k / 2, b = k - a - 1;
+  constexpr int Q4 = TL / 4;
+  for (int idx = threadIdx.x; idx < F * Q4; idx += RN_THREADS) {
+    const int f = idx / Q4, l = 4 * (idx - f * Q4);
+    if (l >= valid) continue;
+    int lo, hi; rn_window(f, F, k, a, b, blocked != 0, lo, hi);
+    const float4 qh = *reinterpret_cast<const float4*>(Q + hi * TL + l), ql = *reinterpret_cast<const float4*>(Q + lo * TL + l);
+    const float4 xv = *reinterpret_cast<const float4*>(X + f * TL + l);
+    float4 r;
+    r.x = xv.x * __powf(1.f + alpha * (qh.x - ql.x), -beta);
+    r.y = xv.y * __powf(1.f + alpha * (qh.y - ql.y), -beta);
+    r.z = xv.z * __powf(1.f + alpha * (qh.z - ql.z), -beta);
+    r.w = xv.w * __powf(1.f + alpha * (qh.w - ql.w), -beta);
+    if (relu) { r.x = fmaxf(r.x, 0.f); r.y = fmaxf(r.y, 0.f); r.z = fmaxf(r.z, 0.f); r.w = fmaxf(r.w, 0.f); }
+    rn_store4(y, y16, (long long)f * L + l0 + l, r, l, valid, vec != 0);
+  }
+}
+
+template <int TL>
+__global__ void __launch_bounds__(RN_THREADS) rnorm_undo_tile_kernel(const float* __restrict__ dy, const float* __restrict__ x,
+                                                                      float* __restrict__ dx, long long L, int F, int k,
+                                                                      float alpha, float beta, int blocked, int vec) {
+  extern __shared__ __align__(16) float sm[];
+  float* X = sm;                               // [F][TL]
+  float* G = X + (size_t)F * TL;               // [F][TL]   dy, then p = dy * base^(-beta)
+  float* Q = G + (size_t)F * TL;               // [F+1][TL] exclusive prefix of x^2
+  float* T = Q + (size_t)(F + 1) * TL;         // [F+1][TL] t = dy * x * base^(-beta-1), then its exclusive prefix
+  float* segtot = T + (size_t)(F + 1) * TL;
+  const long long l0 = (long long)blockIdx.x * TL;
+  const int valid = (int)min((long long)TL, L - l0);
+  rn_load_tile<TL>(X, x, L, l0, F, valid, vec != 0);
+  rn_load_tile<TL>(G, dy, L, l0, F, valid, vec != 0);
+  rn_cp_wait_all();
+  __syncthreads();
+  rn_prefix<TL, true>(X, Q, segtot, F);
+  const int a = k / 2, b = k - a - 1;
+  constexpr int Q4 = TL / 4;
+  for (int idx = threadIdx.x; idx < F * Q4; idx += RN_THREADS) {
+    const int f = idx / Q4, l = 4 * (idx - f * Q4);
+    int lo, hi; rn_window(f, F, k, a, b, blocked != 0, lo, hi);
+    const float4 qh = *reinterpret_cast<const float4*>(Q + hi * TL + l), ql = *reinterpret_cast<const float4*>(Q + lo * TL + l);
+    const float4 xv = *reinterpret_cast<const float4*>(X + f * TL + l), g = *reinterpret_cast<const float4*>(G + f * TL + l);
+    float4 t, p;
+    { const float base = 1.f + alpha * (qh.x - ql.x), den = __powf(base, -beta - 1.f); t.x = g.x * xv.x * den; p.x = g.x * den * base; }
+    { const float base = 1.f + alpha * (qh.y - ql.y), den = __powf(base, -beta - 1.f); t.y = g.y * xv.y * den; p.y = g.y * den * base; }
+    { const float base = 1.f + alpha * (qh.z - ql.z), den = __powf(base, -beta - 1.f); t.z = g.z * xv.z * den; p.z = g.z * den * base; }
+    { const float base = 1.f + alpha * (qh.w - ql.w), den = __powf(base, -beta - 1.f); t.w = g.w * xv.w * den; p.w = g.w * den * base; }
+    *reinterpret_cast<float4*>(T + f * TL + l) = t;
+    *reinterpret_cast<float4*>(G + f * TL + l) = p;
+  }
+  __syncthreads();
+  rn_prefix<TL, false>(T, T, segtot, F);
+  const float c2 = 2.f * alpha * beta;
+  for (int idx = threadIdx.x; idx < F * Q4; idx += RN_THREADS) {
+    const int j = idx / Q4, l = 4 * (idx - j * Q4);
+    if (l >= valid) continue;
+    int lo, hi;                                                       // inverse window: [j-b, j+a]
+    if (blocked) { lo = (j / k) * k; hi = min(F, lo + k); } else { lo = max(0, j - b); hi = min(F, j + a + 1); }
+    const float4 rh = *reinterpret_cast<const float4*>(T + hi * TL + l), rl = *reinterpret_cast<const float4*>(T + lo * TL + l);
+    const float4 xv = *reinterpret_cast<const float4*>(X + j * TL + l), p = *reinterpret_cast<const float4*>(G + j * TL + l);
+    float4 r;
+    r.x = p.x - c2 * xv.x * (rh.x - rl.x); r.y = p.y - c2 * xv.y * (rh.y - rl.y);
+    r.z = p.z - c2 * xv.z * (rh.z - rl.z); r.w = p.w - c2 * xv.w * (rh.w - rl.w);
+    rn_store4(dx, nullptr, (long long)j * L + l0 + l, r, l, valid, vec != 0);
+  }
+}
+
+// tile width for `arrays` F-row arrays (+2 spare rows and the segment totals): the widest of 64 / 32 that lets two CTAs
+// share an SM, else the widest that fits at all; 0 = no tile kernel (window walk with the ring instead)
+static int pick_tile(int F, int arrays, size_t* smem_out) {
+  auto bytes = [&](int tl) { return sizeof(float) * ((size_t)arrays * (F + 1) * tl + RN_THREADS); };
+  const size_t two_per_sm = 110 * 1024, one_per_sm = 220 * 1024;
+  for (int tl : {64, 32}) if (bytes(tl) <= two_per_sm) { *smem_out = bytes(tl); return tl; }
+  for (int tl : {64, 32}) if (bytes(tl) <= one_per_sm) { *smem_out = bytes(tl); return tl; }
+  return 0;
+}
+static bool rn_tile_enabled() {
+  static const bool off = getenv("CONVNET_B200_RNORM_NO_TILE") && getenv("CONVNET_B200_RNORM_NO_TILE")[0] == '1';
+  return !off;
+}
+
 static constexpr size_t kMaxRingSmem = 160 * 1024;
 
 // channel segments per location: 1 unless the location count cannot fill the GPU
@@ -252,9 +430,48 @@ static void launch_fwd(const float* images, float* targets, long long L, int F, 
   kern<<<dim3(blocks, segs), RN_THREADS, smem, state().stream>>>(images, targets, L, F, k, alpha, beta, gring, L, seg);
 }
 
+template <int TL>
+static void launch_fwd_tile(const float* images, float* targets, __nv_bfloat16* t16, long long L, int F, int k, float alpha,
+                            float beta, bool blocked, bool relu, size_t smem, bool vec) {
+  static int attr_dev_mask = 0;
+  const int dev = current_device();
+  if (smem > 48 * 1024 && (dev >= 31 || !((attr_dev_mask >> dev) & 1))) {
+    CNB_CUDA_CHECK(cudaFuncSetAttribute(rnorm_fwd_tile_kernel<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    if (dev < 31) attr_dev_mask |= 1 << dev;
+  }
+  const long long tiles = ceil_div<long long>(L, TL);
+  rnorm_fwd_tile_kernel<TL><<<(unsigned)tiles, RN_THREADS, smem, state().stream>>>(images, targets, t16, L, F, k, alpha, beta,
+                                                                                  blocked ? 1 : 0, relu ? 1 : 0, vec ? 1 : 0);
+}
+template <int TL>
+static void launch_undo_tile(const float* outGrads, const float* inputs, float* targets, long long L, int F, int k, float alpha,
+                             float beta, bool blocked, size_t smem, bool vec) {
+  static int attr_dev_mask = 0;
+  const int dev = current_device();
+  if (smem > 48 * 1024 && (dev >= 31 || !((attr_dev_mask >> dev) & 1))) {
+    CNB_CUDA_CHECK(cudaFuncSetAttribute(rnorm_undo_tile_kernel<TL>, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024));
+    if (dev < 31) attr_dev_mask |= 1 << dev;
+  }
+  const long long tiles = ceil_div<long long>(L, TL);
+  rnorm_undo_tile_kernel<TL><<<(unsigned)tiles, RN_THREADS, smem, state().stream>>>(outGrads, inputs, targets, L, F, k, alpha,
+                                                                                   beta, blocked ? 1 : 0, vec ? 1 : 0);
+}
+
 void rnorm_forward(const float* images, float* targets, long long L, int F, int k, float alpha, float beta,
-                   bool blocked) {
+                   bool blocked, bool relu, __nv_bfloat16* targets_bf16) {
   CNB_REQUIRE(k >= 1 && F >= 1, "ResponseNormCrossMap");
+  size_t tsmem = 0;
+  const int tl = rn_tile_enabled() && L < (1LL << 31) * 32 ? pick_tile(F, 2, &tsmem) : 0;
+  if (tl) {
+    const bool vec = L % 4 == 0 && rn_aligned16(images) && rn_aligned16(targets) &&
+                     (!targets_bf16 || (reinterpret_cast<uintptr_t>(targets_bf16) & 7) == 0);
+    if (tl == 64) launch_fwd_tile<64>(images, targets, targets_bf16, L, F, k, alpha, beta, blocked, relu, tsmem, vec);
+    else launch_fwd_tile<32>(images, targets, targets_bf16, L, F, k, alpha, beta, blocked, relu, tsmem, vec);
+    count_launch();
+    CNB_LAUNCH_CHECK("rnorm_forward(tile)");
+    return;
+  }
+  CNB_REQUIRE(!relu && !targets_bf16, "rnorm_forward: the ring fallback has no fused epilogue (callers check rnorm_can_fuse)");
   // four locations per thread only when that still leaves >= 4 blocks per SM: the channel walk is a serial dependency
   // chain, so small problems need the thread count more than the shorter instruction stream (measured: 105 -> 75 us on
   // 96 x 55 x 55 x 128, but 39 -> 47 us on 256 x 14 x 14 x 128)
@@ -282,9 +499,21 @@ static void launch_undo(const float* outGrads, const float* inputs, float* targe
   kern<<<dim3(blocks, segs), RN_THREADS, smem, state().stream>>>(outGrads, inputs, targets, L, F, k, alpha, beta, gring, L, seg);
 }
 
+bool rnorm_can_fuse(int F) { size_t b; return rn_tile_enabled() && pick_tile(F, 2, &b) != 0; }
+
 void rnorm_undo(const float* outGrads, const float* inputs, float* targets, long long L, int F, int k,
                 float alpha, float beta, bool blocked) {
   CNB_REQUIRE(k >= 1 && F >= 1, "ResponseNormCrossMapUndo");
+  size_t tsmem = 0;
+  const int tl = rn_tile_enabled() ? pick_tile(F, 4, &tsmem) : 0;
+  if (tl) {
+    const bool vec = L % 4 == 0 && rn_aligned16(outGrads) && rn_aligned16(inputs) && rn_aligned16(targets);
+    if (tl == 64) launch_undo_tile<64>(outGrads, inputs, targets, L, F, k, alpha, beta, blocked, tsmem, vec);
+    else launch_undo_tile<32>(outGrads, inputs, targets, L, F, k, alpha, beta, blocked, tsmem, vec);
+    count_launch();
+    CNB_LAUNCH_CHECK("rnorm_undo(tile)");
+    return;
+  }
   // the backward walk carries three rings and two dependent stages per channel: it is latency-bound, and the vector
   // version (a quarter of the threads, 4x the shared memory per block) measured SLOWER (210 -> 333 us); opt-in only
   static const bool wide_undo = getenv("CONVNET_B200_RNORM_UNDO_VEC4") && getenv("CONVNET_B200_RNORM_UNDO_VEC4")[0] == '1';

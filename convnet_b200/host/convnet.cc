@@ -45,28 +45,37 @@ void Layer::AllocateMemory(int batch_size) {               // layer.cc:228-262 (
   }
 }
 
-void Layer::ApplyActivation() {
+// `emit`: this call is the last writer of the tensor and the next conv edge reads it as bf16 (see Edge::SetEmitUp)
+void Layer::ApplyActivation(bool emit) {
   if (activation_fused_) return;
   switch (config_.activation) {
     case LINEAR: break;
-    case RECTIFIED_LINEAR: state_.ApplyReLU(); break;      // LowerBound(0), layer.cc:550
+    case RECTIFIED_LINEAR:
+      if (emit) convnet_b200_emit_bf16_next();
+      state_.ApplyReLU();                                  // LowerBound(0), layer.cc:550
+      break;
     case SOFTMAX: state_.ApplySoftmax(); break;
   }
 }
-void Layer::ApplyDerivativeOfActivation() {
+void Layer::ApplyDerivativeOfActivation(bool emit) {
   if (deriv_fused_) return;
-  if (config_.activation == RECTIFIED_LINEAR) deriv_.ApplyDerivOfReLU(state_);
+  if (config_.activation == RECTIFIED_LINEAR) {
+    if (emit) convnet_b200_emit_bf16_next();
+    deriv_.ApplyDerivOfReLU(state_);
+  }
 }
-void Layer::ApplyDropout(bool train, unsigned long long step, unsigned long long salt) {      // layer.cc:367-395, scale-up at train time
+void Layer::ApplyDropout(bool train, unsigned long long step, unsigned long long salt, bool emit) {      // layer.cc:367-395, scale-up at train time
   if (config_.dropprob <= 0 || !train) return;
+  if (emit) convnet_b200_emit_bf16_next();
   // salt = model seed and data-parallel rank (the reference seeds each process with seed + rank, convnet.cc:67-68):
   // replicas must not draw the same mask for the same local image index
   const unsigned long long seed = (std::hash<std::string>()(config_.name) ^ (step * 0x9E3779B97F4A7C15ULL)) ^ salt;
   cnb_dropout(state_.GetDevData(), dropout_mask_.GetDevData(), (long long)state_.GetNumEls(), config_.dropprob,
               1.0f / (1.0f - config_.dropprob), seed);
 }
-void Layer::ApplyDerivativeofDropout() {
+void Layer::ApplyDerivativeofDropout(bool emit) {
   if (config_.dropprob <= 0 || config_.is_input) return;
+  if (emit) convnet_b200_emit_bf16_next();
   cnb_mult(deriv_.GetDevData(), dropout_mask_.GetDevData(), (long long)deriv_.GetNumEls());
 }
 void Layer::ComputeDeriv() {
@@ -181,7 +190,7 @@ ConvNet::ConvNet(const ModelConfig& model, int batch_size) : model_(model), batc
   if (!(nf && nf[0] == '1')) {
     for (size_t i = 0; i < edges_.size(); i++) {
       Layer *src = layers_[i], *dst = layers_[i + 1];
-      if (dst->GetActivation() == RECTIFIED_LINEAR && model.edge[i].edge_type != RESPONSE_NORM) {
+      if (dst->GetActivation() == RECTIFIED_LINEAR) {
         edges_[i]->SetFuseReLU(true);              // honoured only where CanFuseReLU() (checked after SetImageSize below)
       }
       if (!src->IsInput() && src->GetActivation() == RECTIFIED_LINEAR) edges_[i]->SetFuseMask(true);
@@ -205,12 +214,9 @@ ConvNet::ConvNet(const ModelConfig& model, int batch_size) : model_(model), batc
   }
 }
 
-// Parameters were (or may have been) written outside EdgeWithWeight::UpdateWeights: forget every staged bf16 copy.
-void ConvNet::InvalidateStaging() {
-  convnet_b200_bf16_invalidate(nullptr);
-  for (Edge* e : edges_)
-    if (EdgeWithWeight* w = dynamic_cast<EdgeWithWeight*>(e)) w->MarkWeightsDirty();
-}
+// Parameters (or activations) were, or may have been, written by something the library cannot see (cudaMemcpy, the
+// caller's own kernels): forget every staged bf16 copy.  Writes made through the library keep the copies coherent themselves.
+void ConvNet::InvalidateStaging() { convnet_b200_bf16_invalidate(nullptr); }
 
 ConvNet::~ConvNet() {
   convnet_b200_bf16_invalidate(nullptr);                     // the buffers go away; a later net may get the same addresses
@@ -250,12 +256,18 @@ void ConvNet::AllocateMemory() {
 }
 
 void ConvNet::Fprop(bool train) {                            // convnet.cc:377-388
+  const bool bf16 = convnet_b200_get_conv_precision() == 2;
   for (size_t i = 1; i < layers_.size(); i++) {
     Layer* l = layers_[i];
     Edge* e = edges_[i - 1];
+    // bf16 mode: whoever writes this layer's state LAST (dropout, else a separate activation pass, else the edge's own
+    // kernel) also writes the bf16 copy the next conv edge multiplies with
+    const bool want = bf16 && i < edges_.size() && edges_[i]->WantsBf16Input();
+    const bool drop = train && l->HasDropout(), act_pass = l->HasSeparateActivationPass();
+    e->SetEmitUp(want && !drop && !act_pass);
     e->ComputeUp(layers_[i - 1]->GetState(), l->GetState(), /*overwrite=*/true, train);
-    l->ApplyActivation();
-    l->ApplyDropout(train, step_, dropout_salt_);
+    l->ApplyActivation(want && !drop && act_pass);
+    l->ApplyDropout(train, step_, dropout_salt_, want && drop);
   }
 }
 
@@ -270,14 +282,26 @@ float ConvNet::GetLoss() {                                   // CrossEntropyMult
 }
 
 void ConvNet::Bprop() {                                      // convnet.cc:390-405 + 362-375
+  const bool bf16 = convnet_b200_get_conv_precision() == 2;
   for (int i = (int)layers_.size() - 1; i >= 1; i--) {
     Layer* out = layers_[i];
     Layer* in = layers_[i - 1];
     Edge* e = edges_[i - 1];
+    // bf16 mode: the last writer of a derivative tensor (ReLU' pass, else dropout mask, else the ComputeDown of the edge
+    // above) leaves the bf16 copy the edge below reads in its wgrad and dgrad
     // (the reference runs these two at the top of the NEXT loop iteration, i.e. before this layer's edges)
-    if (!out->IsOutput()) { out->ApplyDerivativeofDropout(); out->ApplyDerivativeOfActivation(); }
+    if (!out->IsOutput()) {
+      const bool want_out = bf16 && e->WantsBf16Deriv();
+      const bool act_pass = out->HasSeparateDerivPass();
+      out->ApplyDerivativeofDropout(want_out && !act_pass);
+      out->ApplyDerivativeOfActivation(want_out && act_pass);
+    }
     e->ComputeOuter(in->GetState(), out->GetDeriv());
-    if (!in->IsInput()) e->ComputeDown(out->GetDeriv(), in->GetState(), out->GetState(), in->GetDeriv(), /*overwrite=*/true);
+    if (!in->IsInput()) {
+      const bool want_in = bf16 && i >= 2 && edges_[i - 2]->WantsBf16Deriv();
+      e->SetEmitDown(want_in && !in->HasDropout() && !in->HasSeparateDerivPass());
+      e->ComputeDown(out->GetDeriv(), in->GetState(), out->GetState(), in->GetDeriv(), /*overwrite=*/true);
+    }
     // data-parallel: ship every bucket whose last gradient just became final (side stream, overlaps the rest of bprop)
     if (dp_ && dp_->world() > 1)
       for (const Bucket& b : buckets_)
@@ -287,7 +311,11 @@ void ConvNet::Bprop() {                                      // convnet.cc:390-4
 
 void ConvNet::UpdateWeights() {                              // convnet.cc:440-450
   if (dp_) dp_->WaitAll();                                   // replaces Accumulate + Broadcast (MPI through host memory)
-  for (Edge* e : edges_) e->UpdateWeights();
+  // one multi-tensor SGD launch for every weight and bias matrix of the net (the reference loops edges: optimizer.cc:174-200)
+  std::vector<CnbSgdTensor> tensors;
+  for (Edge* e : edges_)
+    if (EdgeWithWeight* w = dynamic_cast<EdgeWithWeight*>(e)) w->AppendSgdTensors(tensors);
+  cnb_sgd_momentum_multi(tensors.data(), (int)tensors.size());
 }
 
 void ConvNet::TrainOneBatch(float* loss_out) {               // convnet.cc:475-485 (GetBatch is the caller's H2D copy)

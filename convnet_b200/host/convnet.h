@@ -39,10 +39,13 @@ class Layer {                                   // src/layer.{h,cc}, reduced to 
   explicit Layer(const LayerConfig& c) : config_(c), image_size_y_(0), image_size_x_(0), image_size_t_(1) {}
   void SetSize(int y, int x, int t) { image_size_y_ = y; image_size_x_ = x; image_size_t_ = t; }
   void AllocateMemory(int batch_size);
-  void ApplyActivation();                       // layer.cc:545-560
-  void ApplyDerivativeOfActivation();           // layer.cc:562-580
-  void ApplyDropout(bool train, unsigned long long step, unsigned long long salt);   // layer.cc:  mask = rand > dropprob ; state *= mask
-  void ApplyDerivativeofDropout();
+  void ApplyActivation(bool emit_bf16 = false);               // layer.cc:545-560
+  void ApplyDerivativeOfActivation(bool emit_bf16 = false);   // layer.cc:562-580
+  void ApplyDropout(bool train, unsigned long long step, unsigned long long salt, bool emit_bf16 = false);   // layer.cc:  mask = rand > dropprob ; state *= mask
+  void ApplyDerivativeofDropout(bool emit_bf16 = false);
+  bool HasDropout() const { return config_.dropprob > 0 && !config_.is_input; }
+  bool HasSeparateActivationPass() const { return config_.activation == RECTIFIED_LINEAR && !activation_fused_; }
+  bool HasSeparateDerivPass() const { return config_.activation == RECTIFIED_LINEAR && !deriv_fused_; }
   void ComputeDeriv();                          // softmax + cross-entropy: deriv = p - onehot   (loss_functions.cc)
   Matrix& GetState() { return state_; }
   Matrix& GetDeriv() { return deriv_; }

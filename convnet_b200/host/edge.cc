@@ -73,34 +73,33 @@ void EdgeWithWeight::SetHistoryMemory(Matrix& p) {
 }
 
 void EdgeWithWeight::StageForUp(Matrix& input) {
-  deriv_staged_ = false;
   if (convnet_b200_get_conv_precision() != 2) return;
-  if (bf_up_ == 1 || bf_outer_ == 1) convnet_b200_bf16_stage(input.GetDevData(), (long long)input.GetNumEls());
-  if ((bf_up_ == 1 || bf_down_ == 1) && weights_dirty_) {
-    convnet_b200_bf16_stage(weights_.GetDevData(), (long long)weights_.GetNumEls());
-    weights_dirty_ = false;
-  }
+  if (bf_up_ == 1 || bf_outer_ == 1) convnet_b200_bf16_ensure(input.GetDevData(), (long long)input.GetNumEls());
+  if (bf_up_ == 1 || bf_down_ == 1) convnet_b200_bf16_ensure(weights_.GetDevData(), (long long)weights_.GetNumEls());
 }
 void EdgeWithWeight::StageForBprop(Matrix& deriv_output) {
-  if (deriv_staged_ || convnet_b200_get_conv_precision() != 2) return;
-  if (bf_outer_ == 1 || bf_down_ == 1) convnet_b200_bf16_stage(deriv_output.GetDevData(), (long long)deriv_output.GetNumEls());
-  deriv_staged_ = true;
+  if (convnet_b200_get_conv_precision() != 2) return;
+  if (bf_outer_ == 1 || bf_down_ == 1) convnet_b200_bf16_ensure(deriv_output.GetDevData(), (long long)deriv_output.GetNumEls());
 }
 void EdgeWithWeight::NoteUp() { bf_up_ = convnet_b200_last_conv_path() == 2 ? 1 : 0; }
 void EdgeWithWeight::NoteDown() { bf_down_ = convnet_b200_last_conv_path() == 2 ? 1 : 0; }
 void EdgeWithWeight::NoteOuter() { bf_outer_ = convnet_b200_last_conv_path() == 2 ? 1 : 0; }
 
-void EdgeWithWeight::UpdateWeights() {                       // src/edge_with_weight.cc:96-107 + optimizer.cc:174-200
-  num_grads_received_ = 0;
-  weights_dirty_ = true;
+void EdgeWithWeight::AppendSgdTensors(std::vector<CnbSgdTensor>& out) {   // src/optimizer.cc:174-200 (SGD + momentum + L2)
   const OptimizerConfig& wo = config_.weight_optimizer;
-  cnb_sgd_momentum(weights_.GetDevData(), hist_weights_.GetDevData(), grad_weights_.GetDevData(),
-                   (long long)weights_.GetNumEls(), wo.epsilon, wo.momentum, wo.l2_decay);
+  out.push_back(CnbSgdTensor{weights_.GetDevData(), hist_weights_.GetDevData(), grad_weights_.GetDevData(),
+                             (long long)weights_.GetNumEls(), wo.epsilon, wo.momentum, wo.l2_decay});
   if (!has_no_bias_) {
     const OptimizerConfig& bo = config_.bias_optimizer;
-    cnb_sgd_momentum(bias_.GetDevData(), hist_bias_.GetDevData(), grad_bias_.GetDevData(),
-                     (long long)bias_.GetNumEls(), bo.epsilon, bo.momentum, bo.l2_decay);
+    out.push_back(CnbSgdTensor{bias_.GetDevData(), hist_bias_.GetDevData(), grad_bias_.GetDevData(),
+                               (long long)bias_.GetNumEls(), bo.epsilon, bo.momentum, bo.l2_decay});
   }
+  num_grads_received_ = 0;
+}
+void EdgeWithWeight::UpdateWeights() {                       // src/edge_with_weight.cc:96-107: this edge alone
+  std::vector<CnbSgdTensor> t;
+  AppendSgdTensors(t);
+  cnb_sgd_momentum_multi(t.data(), (int)t.size());
 }
 
 void EdgeWithWeight::Initialize(unsigned seed) {             // DENSE_UNIFORM_SQRT_FAN_IN, edge_with_weight.cc:120-128
@@ -172,6 +171,8 @@ void ConvEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool tra
   const int mods = num_modules_y_ * num_modules_x_ * num_modules_t_;
   const bool fused = fuse_relu_ && CanFuseReLU();        // bias (+ReLU of the destination layer) in the conv epilogue
   StageForUp(input);
+  const bool bias_pass = !has_no_bias_ && !fused;          // then the bias kernel, not the conv, writes the output last
+  if (emit_up_ && !bias_pass) convnet_b200_emit_bf16_next();
   if (image_size_t_ == 1) {
     if (fused) convnet_b200_fuse_next(bias_.GetDevData(), 1, nullptr);
     Matrix::ConvUp(input, weights_, output, conv_desc_, scale_targets);
@@ -182,6 +183,7 @@ void ConvEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool tra
   if (!has_no_bias_ && !fused) {
     if (shared_bias_ && image_size_t_ == 1) {
       output.Reshape(-1, conv_desc_.num_output_channels);
+      if (emit_up_) convnet_b200_emit_bf16_next();
       output.AddRowVec(bias_);
       output.Reshape(-1, conv_desc_.num_output_channels * mods);
     } else if (shared_bias_) {                               // 3-D: per output frame (:157-164)
@@ -203,6 +205,7 @@ void ConvEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, 
   const float scale_targets = overwrite ? 0 : 1;
   StageForBprop(deriv_output);
   if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());      // ReLU' of the source layer
+  if (emit_down_) convnet_b200_emit_bf16_next();
   if (image_size_t_ == 1) Matrix::ConvDown(deriv_output, weights_, deriv_input, conv_desc_, scale_targets);
   else Matrix::Conv3DDown(deriv_output, weights_, deriv_input, conv_desc_, scale_targets);
   NoteDown();
@@ -287,9 +290,11 @@ void FCEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train
   const bool fused = fuse_relu_ && !has_no_bias_;
   StageForUp(input);
   if (fused) convnet_b200_fuse_next(bias_.GetDevData(), 1, nullptr);
+  const bool bias_pass = !has_no_bias_ && !fused;
+  if (emit_up_ && !bias_pass) convnet_b200_emit_bf16_next();
   Matrix::ConvUp(input, weights_, output, desc_, overwrite ? 0 : 1);     // output = input * W^T
   NoteUp();
-  if (!has_no_bias_ && !fused) output.AddRowVec(bias_);
+  if (bias_pass) { if (emit_up_) convnet_b200_emit_bf16_next(); output.AddRowVec(bias_); }
   input.GetShape4D() = si; output.GetShape4D() = so;
 }
 void FCEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) {
@@ -297,6 +302,7 @@ void FCEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Ma
   View(deriv_input, deriv_output);
   StageForBprop(deriv_output);
   if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
+  if (emit_down_) convnet_b200_emit_bf16_next();
   Matrix::ConvDown(deriv_output, weights_, deriv_input, desc_, overwrite ? 0 : 1);
   NoteDown();
   deriv_input.GetShape4D() = si; deriv_output.GetShape4D() = so;
@@ -340,10 +346,13 @@ void ConvOneToOneEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, 
   const bool fused = fuse_relu_ && !has_no_bias_;
   StageForUp(input);
   if (fused) convnet_b200_fuse_next(bias_.GetDevData(), 1, nullptr);
+  const bool bias_pass = !has_no_bias_ && !fused;
+  if (emit_up_ && !bias_pass) convnet_b200_emit_bf16_next();
   Matrix::ConvUp(input, weights_, output, desc_, overwrite ? 0 : 1);
   NoteUp();
   if (!has_no_bias_ && !fused) {
     output.Reshape(-1, num_output_channels_);
+    if (emit_up_) convnet_b200_emit_bf16_next();
     output.AddRowVec(bias_);
     output.Reshape(batch_size, -1);
   }
@@ -352,6 +361,7 @@ void ConvOneToOneEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& 
                                    bool overwrite) {
   StageForBprop(deriv_output);
   if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
+  if (emit_down_) convnet_b200_emit_bf16_next();
   Matrix::ConvDown(deriv_output, weights_, deriv_input, desc_, overwrite ? 0 : 1);
   NoteDown();
 }
@@ -389,18 +399,22 @@ void MaxPoolEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool 
     fprintf(stderr, " In MaxPoolEdge::ComputeUp() : some other layer is writing to this maxpool layer's output. Not implemented.\n");
     exit(1);
   }
+  if (emit_up_) convnet_b200_emit_bf16_next();
   Matrix::ConvMaxPool(input, output, conv_desc_);
 }
 void MaxPoolEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) {
   if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
+  if (emit_down_) convnet_b200_emit_bf16_next();
   Matrix::ConvMaxPoolUndo(input, deriv_output, output, deriv_input, conv_desc_, overwrite ? 0 : 1);
 }
 void AvgPoolEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) {   // avgpool_edge.cc:50-58
   if (!overwrite) { fprintf(stderr, " In AvgPoolEdge::ComputeUp() : not implemented for non-overwrite.\n"); exit(1); }
+  if (emit_up_) convnet_b200_emit_bf16_next();
   Matrix::ConvAvgPool(input, output, conv_desc_);
 }
 void AvgPoolEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) {
   if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
+  if (emit_down_) convnet_b200_emit_bf16_next();
   Matrix::ConvAvgPoolUndo(deriv_output, deriv_input, conv_desc_, overwrite ? 0 : 1);
 }
 
@@ -410,6 +424,8 @@ void ResponseNormEdge::SetImageSize(int y, int x, int t) {   // :32-39
   num_filters_response_norm_ = (int)(frac_of_filters_response_norm_ * num_input_channels_);
 }
 void ResponseNormEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) {   // :41-51
+  if (fuse_relu_ && image_size_t_ == 1) convnet_b200_fuse_next(nullptr, 1, nullptr);     // ReLU of the destination layer
+  if (emit_up_) convnet_b200_emit_bf16_next();
   if (image_size_t_ == 1)
     Matrix::ConvResponseNormCrossMap(input, output, num_input_channels_, num_filters_response_norm_, add_scale_, pow_scale_, blocked_);
   else
@@ -417,6 +433,7 @@ void ResponseNormEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, 
 }
 void ResponseNormEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input,
                                    bool overwrite) {         // :53-66 (ignores `overwrite`, like the reference)
+  if (emit_down_) convnet_b200_emit_bf16_next();
   if (image_size_t_ == 1)
     Matrix::ConvResponseNormCrossMapUndo(deriv_output, input, output, deriv_input, num_input_channels_, num_filters_response_norm_, add_scale_, pow_scale_, blocked_);
   else

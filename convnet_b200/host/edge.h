@@ -89,6 +89,14 @@ class Edge {
   void SetFuseMask(bool v) { fuse_mask_ = v; }
   bool WantsFuseReLU() const { return fuse_relu_; }
   bool WantsFuseMask() const { return fuse_mask_; }
+  // bf16 mode: the kernel that writes a tensor LAST also leaves its bf16 copy for the conv edge that reads it next
+  // (convnet_b200_emit_bf16_next) instead of that edge running a conversion pass.  ConvNet sets these before each call:
+  // emit_up: ComputeUp is the last writer of the destination state and the next edge multiplies in bf16;
+  // emit_down: ComputeDown is the last writer of the source layer's derivative and the edge below multiplies in bf16.
+  void SetEmitUp(bool v) { emit_up_ = v; }
+  void SetEmitDown(bool v) { emit_down_ = v; }
+  virtual bool WantsBf16Input() const { return false; }      // this edge reads its input (fprop / wgrad) as bf16
+  virtual bool WantsBf16Deriv() const { return false; }      // this edge reads its output derivative (wgrad / dgrad) as bf16
 
  protected:
   EdgeConfig config_;
@@ -99,6 +107,7 @@ class Edge {
   int num_modules_y_, num_modules_x_, num_modules_t_;
   int batch_size_;
   bool fuse_relu_ = false, fuse_mask_ = false;
+  bool emit_up_ = false, emit_down_ = false;
 };
 
 class EdgeWithWeight : public Edge {
@@ -116,11 +125,14 @@ class EdgeWithWeight : public Edge {
   void IncrementNumGradsReceived() { num_grads_received_++; }
   void NotifyStart() { num_grads_received_ = 0; }
   virtual int FanIn() const = 0;
-  // bf16 mode (convnet_b200_set_conv_precision(2)): each tensor this edge feeds to two conv calls of a step is converted
-  // once through convnet_b200_bf16_stage — the input (fprop + wgrad), the output derivative (wgrad + dgrad) and the
-  // weights (fprop + dgrad, re-staged after every update).  Which calls really run in bf16 is learnt from
-  // convnet_b200_last_conv_path() during the first step (FC-shaped calls stay on tf32 and are not staged).
-  void MarkWeightsDirty() { weights_dirty_ = true; }
+  // bf16 mode (convnet_b200_set_conv_precision(2)): each tensor this edge feeds to two conv calls of a step has ONE bf16
+  // copy — the input (fprop + wgrad), the output derivative (wgrad + dgrad) and the weights (fprop + dgrad).  The copy is
+  // normally written by the kernel that produced the tensor (emit_up / emit_down of the neighbouring edges, the dropout
+  // and SGD kernels); convnet_b200_bf16_ensure converts only when no valid copy exists.  Which calls really run in bf16 is
+  // learnt from convnet_b200_last_conv_path() during the first step (FC-shaped calls stay on tf32 and are not staged).
+  bool WantsBf16Input() const override { return bf_up_ == 1 || bf_outer_ == 1; }
+  bool WantsBf16Deriv() const override { return bf_outer_ == 1 || bf_down_ == 1; }
+  void AppendSgdTensors(std::vector<CnbSgdTensor>& out);                 // weights (+ bias) of this edge for one multi-tensor update
 
  protected:
   void StageForUp(Matrix& input);
@@ -133,7 +145,6 @@ class EdgeWithWeight : public Edge {
   float scale_gradients_;
   int num_grads_received_;
   int bf_up_ = -1, bf_down_ = -1, bf_outer_ = -1;        // -1 unknown, 0 tf32 / fp32 path, 1 bf16 path
-  bool weights_dirty_ = true, deriv_staged_ = false;
 };
 
 class ConvEdge : public EdgeWithWeight {
@@ -219,6 +230,7 @@ class AvgPoolEdge : public MaxPoolEdge {
 
 class ResponseNormEdge : public Edge {
  public:
+  bool CanFuseReLU() const override { return image_size_t_ == 1; }      // max(., 0) rides in the rnorm kernel's store
   explicit ResponseNormEdge(const EdgeConfig& c)
       : Edge(c), num_filters_response_norm_(0), blocked_(c.response_norm_in_blocks), add_scale_(c.add_scale),
         pow_scale_(c.pow_scale), frac_of_filters_response_norm_(c.frac_of_filters_response_norm) {}

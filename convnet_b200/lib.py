@@ -73,6 +73,9 @@ SIGNATURES = {
     "convnet_b200_launch_count": [],
     "convnet_b200_fuse_next": [FP, I, FP],
     "convnet_b200_bf16_stage": [FP, ct.c_longlong],
+    "convnet_b200_bf16_ensure": [FP, ct.c_longlong],
+    "convnet_b200_bf16_is_staged": [FP, ct.c_longlong],
+    "convnet_b200_emit_bf16_next": [],
     "convnet_b200_bf16_invalidate": [FP],
     "convnet_b200_reset_launch_count": [],
     "convnet_b200_release_workspace": [],
@@ -82,6 +85,7 @@ SIGNATURES = {
     "cnb_relu": [FP, ct.c_longlong],
     "cnb_relu_deriv": [FP, FP, ct.c_longlong],
     "cnb_sgd_momentum": [FP, FP, FP, ct.c_longlong, F, F, F],
+    "cnb_sgd_momentum_multi": [ct.c_void_p, I],
     "cnb_dropout": [FP, FP, ct.c_longlong, F, F, ct.c_ulonglong],
     "cnb_mult": [FP, FP, ct.c_longlong],
     "cnb_softmax": [FP, I, I],
@@ -90,7 +94,7 @@ SIGNATURES = {
 }
 RESTYPES = {
     "convnet_b200_version": I, "convnet_b200_get_stream": ct.c_void_p,
-    "convnet_b200_get_conv_precision": I, "convnet_b200_last_conv_path": I,
+    "convnet_b200_get_conv_precision": I, "convnet_b200_last_conv_path": I, "convnet_b200_bf16_is_staged": I,
     "convnet_b200_launch_count": ct.c_ulonglong,
 }
 

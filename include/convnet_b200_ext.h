@@ -24,13 +24,13 @@ void convnet_b200_set_stream(void* cuda_stream);
 void* convnet_b200_get_stream(void);
 
 /* Arithmetic of the three conv ops (pool / response-norm are always fp32):
- *   0  FP32  fp32 FMA on CUDA cores; meets the reference's own 1e-4 kernel test
- *            tolerance (py/test_conv.py:387) and is what run_grad_check should use
- *   1  TF32  tcgen05 kind::tf32 on the caller's fp32 buffers, fp32 accumulate (default);
+ *   0  FP32  fp32 FMA on CUDA cores (the DEFAULT: a drop-in caller gets the reference's arithmetic); meets the
+ *            reference's own 1e-4 kernel test tolerance (py/test_conv.py:387); what run_grad_check uses
+ *   1  TF32  tcgen05 kind::tf32 on the caller's fp32 buffers, fp32 accumulate;
  *            Diff <= 5e-3 (operands truncated to 10 mantissa bits by the tensor core)
  *   2  BF16  tcgen05 kind::f16 on bf16 copies, fp32 accumulate; Diff <= 2e-2
- * Shapes the tensor-core path does not take fall through to FP32.  Also settable
- * with CONVNET_B200_PRECISION={fp32,tf32,bf16} before first use. */
+ * Shapes the tensor-core path does not take fall through to FP32.  The tensor-core modes are opt-in: this call, or
+ * CONVNET_B200_PRECISION={fp32,tf32,bf16} in the environment before first use (host/ConvNet and bench.py opt in). */
 void convnet_b200_set_conv_precision(int mode);
 int convnet_b200_get_conv_precision(void);
 
@@ -58,11 +58,25 @@ void convnet_b200_fuse_next(const float* bias, int relu, const float* relu_mask)
  * its two fp32 operands to bf16 copies.  A caller that knows a tensor stays unchanged across several conv calls
  * (the layer input: fprop + wgrad; the output derivative: wgrad + dgrad; the weights: fprop + dgrad) can have it
  * converted ONCE: convnet_b200_bf16_stage(ptr, n) converts the n floats at ptr now (stream-ordered) and conv calls
- * that receive exactly `ptr` as an operand use that copy until the next _stage / _invalidate of the same pointer.
- * The CALLER owns coherence: after writing to a staged tensor it must stage it again or invalidate it.
- * convnet_b200_bf16_invalidate(NULL) forgets every staged tensor. */
+ * that receive exactly `ptr` as an operand use that copy while it is valid.  convnet_b200_bf16_ensure converts only
+ * when no valid copy exists.
+ * Coherence: every entry point of THIS library that writes a tensor drops the staged copies overlapping what it
+ * writes (and convnet_b200_emit_bf16_next makes it leave a fresh one), and cnb_sgd_momentum refreshes the copy of
+ * the weights it updates.  Only writes the library cannot see (cudaMemcpy, another library's kernels) need an
+ * explicit convnet_b200_bf16_invalidate(ptr) / _stage(ptr, n) from the caller; convnet_b200_bf16_invalidate(NULL)
+ * forgets every staged tensor.  CONVNET_B200_STAGE_VERIFY=1 (environment) re-converts the fp32 source at every use of
+ * a staged copy and aborts on a mismatch — the way to find such a missed write. */
 void convnet_b200_bf16_stage(const float* ptr, long long n);
+void convnet_b200_bf16_ensure(const float* ptr, long long n);
 void convnet_b200_bf16_invalidate(const float* ptr);
+int convnet_b200_bf16_is_staged(const float* ptr, long long n);   /* 1 if a valid staged copy covers [ptr, ptr+n) */
+
+/* One-shot: the NEXT entry point of this library that writes a tensor (conv fprop / dgrad, pooling and its undo,
+ * response norm and its undo, cnb_relu, cnb_dropout, cnb_mult, cnb_add_channel_bias*) also leaves a staged bf16 copy of
+ * the WHOLE target tensor, exactly as convnet_b200_bf16_stage(target, n) right after the call would — but written by the
+ * producing kernel from the same registers where that kernel supports it (the fp32 -> bf16 pass and its 6 bytes/element
+ * of HBM traffic disappear), by a trailing conversion pass where it does not.  No-op outside bf16 mode. */
+void convnet_b200_emit_bf16_next(void);
 
 /* ---- steps either side of the conv ops that the Edge layer sequences ------------
  * (in the reference these are libcudamat.so calls:
@@ -98,6 +112,13 @@ void cnb_sum(const float* a, float* out, int n);
  *   g' = lr*(g + l2*w);  h = momentum*h + g';  w -= h */
 void cnb_sgd_momentum(float* w, float* hist, const float* grad, long long n, float lr,
                       float momentum, float l2);
+/* the same update for `count` tensors in ONE launch (one call per all-reduce bucket / per net instead of one per
+ * weight and bias matrix).  `tensors` is a host array.  In bf16 mode a staged copy of a weight tensor is refreshed
+ * by the same pass (see convnet_b200_bf16_stage). */
+typedef struct CnbSgdTensor {
+  float* w; float* hist; const float* grad; long long n; float lr, momentum, l2;
+} CnbSgdTensor;
+void cnb_sgd_momentum_multi(const CnbSgdTensor* tensors, int count);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop
