@@ -73,6 +73,7 @@ struct State {
   int ws_device = -1;
   int num_sms = 0;
   int sm_device = -1;
+  int sm_reserve = 0;                 // SMs the persistent conv grids leave free (convnet_b200_reserve_sms)
   Fuse fuse;
 };
 inline Fuse take_fuse();

@@ -71,11 +71,16 @@ struct TcParams {
                                     // fprop/dgrad of 1x1 / FC shapes with few tiles: K blocks per split (split-K)
   long long part_stride;            // fprop/dgrad split-K: floats between the partial outputs of consecutive splits
   float* out;
+  __nv_bfloat16* out16;             // optional bf16 twin of `out` (same indexing): convnet_b200_emit_bf16_next
   float st, so;
   const float* bias; int relu;      // fused fprop epilogue: + bias[o], then max(., 0)
   const float* mask;                // fused dgrad epilogue: zero where mask <= 0 (same layout as out)
   long long out_frame_step;         // fprop: floats between output frames
   uint32_t idesc;
+  // fast kernels (tc_fast_kernel): bf16, one-request A tiles, K per pipeline stage = 16 * ksteps elements
+  int ksteps;                       // UMMA K-steps per stage: 4 (64 K elements) or 8 (128)
+  uint32_t a_stage_bytes;           // 128 rows x (16 * ksteps) bf16
+  int b_chunks;                     // fprop: 64-column chunks of B this CTA stages per k-block
 };
 
 struct __align__(8) SmemCtl {
@@ -84,6 +89,7 @@ struct __align__(8) SmemCtl {
   uint64_t tmem_full[2];
   uint64_t tmem_empty[2];
   uint32_t tmem_base;
+  int tile_nkb[16];                 // fast kernels: k-blocks of the tile, producer -> MMA issuer (ring over tiles; the producer runs <= 9 tiles ahead)
 };
 
 // ------------------------------------------------------------------------------------------------
@@ -544,6 +550,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           }
         } else if (fused) {
           float* dst = row_ptr + col_stride * j0;
+          __nv_bfloat16* dst16 = p.out16 ? p.out16 + (dst - p.out) : nullptr;
           // all 32 auxiliary loads (bias values / mask elements) are issued before the first dependent store;
           // interleaving them with the stores serialised one memory latency per column
           float aux[32];
@@ -566,17 +573,28 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
                 if (p.relu) r = fmaxf(r, 0.f);
               } else if (!(aux[j] > 0.f)) r = 0.f;
               *dst = r;
+              if (dst16) dst16[col_stride * j] = __float2bfloat16_rn(r);
             }
         } else if (rmw) {
           float* dst = row_ptr + col_stride * j0;
+          __nv_bfloat16* dst16 = p.out16 ? p.out16 + (dst - p.out) : nullptr;
 #pragma unroll
           for (int j = 0; j < 32; j++, dst += col_stride)
-            if (j < nv) *dst = p.st * (*dst) + so_eff * v[j];
+            if (j < nv) {
+              const float r = p.st * (*dst) + so_eff * v[j];
+              *dst = r;
+              if (dst16) dst16[col_stride * j] = __float2bfloat16_rn(r);
+            }
         } else {
           float* dst = row_ptr + col_stride * j0;
+          __nv_bfloat16* dst16 = p.out16 ? p.out16 + (dst - p.out) : nullptr;
 #pragma unroll
           for (int j = 0; j < 32; j++, dst += col_stride)
-            if (j < nv) *dst = so_eff * v[j];
+            if (j < nv) {
+              const float r = so_eff * v[j];
+              *dst = r;
+              if (dst16) dst16[col_stride * j] = __float2bfloat16_rn(r);
+            }
         }
       }
       ptx::tc_fence_before();
@@ -594,6 +612,340 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   if (warp == 1) {
     ptx::tc_fence_after();
     if constexpr (cta2) ptx::tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
+    else ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
+  }
+}
+
+
+// ================================================================================================
+// tc_fast_kernel — the same three implicit GEMMs, specialised for the shapes the training step spends its time in.
+//
+// ncu on the general kernel above (profiles/r2_conv2_dgrad_ncu.md) showed where the time goes: NOT the tensor pipe (16-54 %
+// active), not L2 (< 30 %), but the single producer warp — 55-80 dependent uniform-datapath instructions per k-block
+// (run-time layout switches, 64-bit address arithmetic, per-tap divisions, vote/R2UR traffic around every TMA issue) and the
+// same again in the MMA-issuing warp, with the per-tile tap decode on top.  This kernel removes the switches at compile time:
+//   * bf16 operands only; every A tile is ONE TMA request (N % 128 == 0); channel counts are multiples of 32;
+//     2-D, no split-K, overwrite (scaleTargets == 0); anything else still takes the general kernel;
+//   * K per pipeline stage is 64 OR 128 elements (ksteps 4 / 8): half the barrier round trips and TMA issues per flop
+//     whenever three 128-deep stages fit in shared memory;
+//   * the producer and MMA loops work on 32-bit shared-window addresses that advance by adds; waits have an out-of-line
+//     slow path; the producer hands the k-block count of each tile to the MMA warp through shared memory instead of both
+//     decoding the tile; dgrad live taps are arithmetic progressions (first tap, count) computed once per tile.
+// Pipeline, barriers, TMEM double buffering and the CTA-pair protocol are those of tc_conv_kernel.
+// ================================================================================================
+struct FastTile {
+  int nkb;                          // k-blocks of this tile (>= 1)
+  int a2, a3, a4;                   // A coordinates that are fixed for the tile (meaning depends on OP)
+  int n0, n1;                       // loop counts of the two outer k-loop levels
+  int t0;                           // first tap (dgrad) / unused
+  int b0;                           // B coordinate fixed for the tile
+};
+
+template <int OP, bool PAIR>
+__global__ void __launch_bounds__(kThreads, 1)
+tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int rank = PAIR ? (int)(blockIdx.x & 1u) : 0;               // clusters are (2,1,1): the rank is the parity of blockIdx.x
+  const uint32_t b_stage_bytes = (uint32_t)p.b_rows * 128u;
+  uint8_t* smemA = smem;
+  uint8_t* smemB = smem + (size_t)p.stages * p.a_stage_bytes;
+  SmemCtl* ctl = reinterpret_cast<SmemCtl*>(smemB + (size_t)p.stages * b_stage_bytes);
+  const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; s++) { ptx::mbar_init(&ctl->full[s], 1); ptx::mbar_init(&ctl->empty[s], 1); }
+    for (int a = 0; a < 2; a++) { ptx::mbar_init(&ctl->tmem_full[a], 1); ptx::mbar_init(&ctl->tmem_empty[a], PAIR ? 8 : 4); }
+    ptx::fence_barrier_init();
+    ptx::tma_prefetch_desc(&mapA);
+    ptx::tma_prefetch_desc(&mapB);
+  }
+  if (warp == 1) {
+    if constexpr (PAIR) { ptx::tmem_alloc_2sm(&ctl->tmem_base, (uint32_t)p.tmem_cols); ptx::tmem_relinquish_2sm(); }
+    else { ptx::tmem_alloc(&ctl->tmem_base, (uint32_t)p.tmem_cols); ptx::tmem_relinquish(); }
+  }
+  ptx::tc_fence_before();
+  if constexpr (PAIR) ptx::cluster_sync(); else __syncthreads();
+  ptx::tc_fence_after();
+  const int t_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int t_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const uint32_t tmem_base = ctl->tmem_base;
+  const int bn_local = PAIR ? p.BN / 2 : p.BN;
+  const int bk = p.ksteps * 16;                                     // K elements per stage
+  const uint32_t bar_full0 = ptx::smem_u32(&ctl->full[0]), bar_empty0 = ptx::smem_u32(&ctl->empty[0]);
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    const bool elected = ptx::elect_one();
+    const uint32_t a_base = ptx::smem_u32(smemA), b_base = ptx::smem_u32(smemB);
+    const uint32_t tx_bytes = (p.a_stage_bytes + p.b_tx_bytes) * (PAIR ? 2u : 1u);
+    uint32_t stage = 0, phase = 0, a_addr = a_base, b_addr = b_base, bar_off = 0;
+    int tcount = 0;
+    // one pipeline slot: wait until the MMAs that read it have retired, arm the barrier, return the addresses to fill
+#define CNB_STAGE_BEGIN()                                                                              \
+    ptx::mbar_wait_a(bar_empty0 + bar_off, phase ^ 1u);                                                \
+    const uint32_t fullb = PAIR ? ptx::leader_addr(bar_full0 + bar_off) : (bar_full0 + bar_off);       \
+    if (elected && rank == 0) ptx::mbar_arrive_expect_tx_a(bar_full0 + bar_off, tx_bytes);
+#define CNB_STAGE_END()                                                                                \
+    a_addr += p.a_stage_bytes; b_addr += b_stage_bytes; bar_off += 8;                                  \
+    if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; a_addr = a_base; b_addr = b_base; bar_off = 0; }
+
+    for (int t = t_first; t < p.num_tiles; t += t_step, tcount++) {
+      if (OP == kFprop) {
+        const int n_tile = t % p.n_tiles, mg = t / p.n_tiles;
+        const int m_tile = PAIR ? 2 * mg + rank : mg;
+        const int q = m_tile * 2;                                     // first 64-image chunk of the tile
+        const bool ok = q < p.total_chunks;
+        const int ib = q % p.nbc, pos = q / p.nbc;
+        const int n_hi = ok ? ib : p.nbc;                             // out of range: the whole box zero-fills
+        const int cX = (pos % p.modX) * p.sx + p.px, cY = (pos / p.modX) * p.sy + p.py;
+        const int o0 = n_tile * p.BN + rank * bn_local;
+        if (elected) ctl->tile_nkb[tcount & 15] = p.taps * p.kc_blocks;
+        int tap = 0;
+        for (int ty = 0; ty < p.ky; ty++)
+          for (int tx = 0; tx < p.kx; tx++, tap++)
+            for (int c = 0; c < p.Cin; c += bk) {
+              CNB_STAGE_BEGIN();
+              if (elected) {
+                ptx::tma5_a<PAIR>(&mapA, fullb, a_addr, 0, c, n_hi, cX + tx, cY + ty);            // dims (n_lo, c, n_hi, x, y)
+                if (p.b_merged) ptx::tma4_a<PAIR>(&mapB, fullb, b_addr, 0, c, o0 >> 6, tap);     // dims (o_lo, c, o_hi, tap)
+                else
+                  for (int j = 0; j < p.b_chunks; j++)                                             // dims (o, tap, c)
+                    ptx::tma3_a<PAIR>(&mapB, fullb, b_addr + (uint32_t)j * (uint32_t)(bk * 128), o0 + j * 64, tap, c);
+              }
+              CNB_STAGE_END();
+            }
+      } else if (OP == kDgrad) {
+        const int n_tile = t % p.n_tiles, mg = t / p.n_tiles;
+        const int m_tile = PAIR ? 2 * mg + rank : mg;
+        const int q = m_tile * 2;
+        const bool ok = q < p.total_chunks;
+        const int ib = q % p.nbc, pos = q / p.nbc;
+        const int n_hi = ok ? ib : p.nbc;
+        // live taps along x: t = tx0 + i*sx, i < ntx, reading module mx0 - i  (cudamat_conv_gemm.cu:684-825: the gather form
+        // of kContract); dead taps are skipped, not multiplied by zero
+        const int X = pos % p.W, Y = pos / p.W;
+        int tx0, ntx, mx0, ty0, nty, my0;
+        {
+          const int a = X - p.px;                                      // >= 0 (px <= 0)
+          const int lo = max(a - (p.modX - 1) * p.sx, 0);               // smallest tap whose module index is <= modX-1
+          const int r = a % p.sx;
+          tx0 = lo + ((r - lo) % p.sx + p.sx) % p.sx;                  // first tap >= lo congruent to a (mod sx)
+          const int hi = min(p.kx - 1, a);
+          ntx = hi >= tx0 ? (hi - tx0) / p.sx + 1 : 0;
+          mx0 = (a - tx0) / p.sx;
+        }
+        {
+          const int a = Y - p.py;
+          const int lo = max(a - (p.modY - 1) * p.sy, 0);
+          const int r = a % p.sy;
+          ty0 = lo + ((r - lo) % p.sy + p.sy) % p.sy;
+          const int hi = min(p.ky - 1, a);
+          nty = hi >= ty0 ? (hi - ty0) / p.sy + 1 : 0;
+          my0 = (a - ty0) / p.sy;
+        }
+        if (!ok || ntx == 0 || nty == 0) { ntx = 1; nty = 1; tx0 = 0; ty0 = 0; mx0 = -1; my0 = -1; }   // one all-zero group
+        const int c0 = n_tile * p.BN + rank * bn_local;
+        if (elected) ctl->tile_nkb[tcount & 15] = ntx * nty * p.kc_blocks;
+        for (int iy = 0; iy < nty; iy++)
+          for (int ix = 0; ix < ntx; ix++) {
+            const int tap = (tx0 + ix * p.sx) + p.kx * (ty0 + iy * p.sy);
+            for (int o = 0; o < p.Cout; o += bk) {
+              CNB_STAGE_BEGIN();
+              if (elected) {
+                ptx::tma5_a<PAIR>(&mapA, fullb, a_addr, 0, o, n_hi, mx0 - ix, my0 - iy);          // dims (n_lo, o, n_hi, mx, my)
+                ptx::tma3_a<PAIR>(&mapB, fullb, b_addr, o, tap, c0);                               // dims (o, tap, c): 64 o per panel
+                if (p.ksteps == 8) ptx::tma3_a<PAIR>(&mapB, fullb, b_addr + (uint32_t)bn_local * 128u, o + 64, tap, c0);
+              }
+              CNB_STAGE_END();
+            }
+          }
+      } else {
+        // wgrad tile (tap, o_tile, c_tile, split): sum over the module rows of this split whose tap lands inside the image
+        int tt = t;
+        const int split = tt % p.splits; tt /= p.splits;
+        const int c_tile = tt % p.n_tiles; tt /= p.n_tiles;
+        int o_tile = tt % p.m_groups; tt /= p.m_groups;
+        if (PAIR) o_tile = 2 * o_tile + rank;
+        const int tx = tt % p.kx, ty = tt / p.kx;
+        int r0 = split * p.units_per_split, r1 = min(r0 + p.units_per_split, p.modY);
+        // rows: 0 <= my*sy + py + ty < H ; columns likewise
+        const int ylo = -(p.py + ty), yhi = p.H - 1 - p.py - ty;
+        r0 = max(r0, ylo <= 0 ? 0 : (ylo + p.sy - 1) / p.sy);
+        r1 = min(r1, yhi < 0 ? 0 : yhi / p.sy + 1);
+        const int xlo = -(p.px + tx), xhi = p.W - 1 - p.px - tx;
+        const int mx_lo = xlo <= 0 ? 0 : (xlo + p.sx - 1) / p.sx;
+        const int mx_hi = xhi < 0 ? -1 : min(xhi / p.sx, p.modX - 1);
+        const int nmx = max(mx_hi - mx_lo + 1, 0), nrow = max(r1 - r0, 0);
+        const int cps = p.ksteps >> 2;                                  // 64-image chunks per stage (1 or 2)
+        const int nsteps = p.nbc / cps;
+        const bool none = nmx == 0 || nrow == 0;
+        if (elected) ctl->tile_nkb[tcount & 15] = none ? nsteps : nrow * nmx * nsteps;
+        const int o0 = o_tile * BM, c0 = c_tile * p.BN + rank * bn_local;
+        if (none) {
+          for (int ib = 0; ib < nsteps; ib++) {                         // nothing to sum: one group of zero k-blocks
+            CNB_STAGE_BEGIN();
+            if (elected) {
+              ptx::tma5_a<PAIR>(&mapA, fullb, a_addr, 0, -1, -1, o0, cps * ib);
+              ptx::tma5_a<PAIR>(&mapB, fullb, b_addr, 0, -1, -1, c0, cps * ib);
+            }
+            CNB_STAGE_END();
+          }
+        } else {
+          for (int my = r0; my < r1; my++) {
+            const int Yc = my * p.sy + p.py + ty;
+            for (int mx = mx_lo; mx <= mx_hi; mx++) {
+              const int Xc = mx * p.sx + p.px + tx;
+              for (int ib = 0; ib < nsteps; ib++) {
+                CNB_STAGE_BEGIN();
+                if (elected) {
+                  ptx::tma5_a<PAIR>(&mapA, fullb, a_addr, 0, mx, my, o0, cps * ib);               // dims (n_lo, mx, my, o, n_hi)
+                  ptx::tma5_a<PAIR>(&mapB, fullb, b_addr, 0, Xc, Yc, c0, cps * ib);               // dims (n_lo, x, y, c, n_hi)
+                }
+                CNB_STAGE_END();
+              }
+            }
+          }
+        }
+      }
+    }
+#undef CNB_STAGE_BEGIN
+#undef CNB_STAGE_END
+  } else if (warp == 1 && rank == 0) {
+    // =============================== MMA issuer (leader CTA only in pair mode) ===
+    // operand layouts exactly as in tc_conv_kernel; K-steps inside a stage: MN-major operands advance by 16 rows of 128 B,
+    // K-major ones by 32 B inside a 64-element panel and by one panel (rows * 128 B) after four steps
+    const bool a_mn = (OP != kWgrad), b_mn = (OP == kFprop);
+    const uint32_t mn_lbo = (uint32_t)bk * 128u;
+    const uint32_t b_rows_local = (uint32_t)bn_local;
+    const uint64_t da_base = ptx::make_smem_desc(ptx::smem_u32(smemA), a_mn ? mn_lbo : 16u, 1024u, ptx::kLayoutSw128);
+    const uint64_t db_base = ptx::make_smem_desc(ptx::smem_u32(smemB), b_mn ? mn_lbo : 16u, 1024u, ptx::kLayoutSw128);
+    const uint32_t a_lo = a_mn ? 128u : 2u, a_hi = a_mn ? 512u : (uint32_t)(BM * 128 >> 4);          // descriptor units of 16 B
+    const uint32_t b_lo = b_mn ? 128u : 2u, b_hi = b_mn ? 512u : (b_rows_local * 128u) >> 4;
+    const uint32_t a_stage_u = p.a_stage_bytes >> 4, b_stage_u = b_stage_bytes >> 4;
+    const bool elected = ptx::elect_one();
+    uint32_t stage = 0, phase = 0, bar_off = 0, a_off = 0, b_off = 0;
+    uint32_t acc = 0, acc_phase = 0;
+    int tcount = 0;
+    const uint32_t tfull0 = ptx::smem_u32(&ctl->tmem_full[0]), tempty0 = ptx::smem_u32(&ctl->tmem_empty[0]);
+    for (int t = t_first; t < p.num_tiles; t += t_step, tcount++) {
+      ptx::mbar_wait_a(tempty0 + acc * 8, acc_phase ^ 1u);
+      ptx::tc_fence_after();
+      const uint32_t d_tmem = tmem_base + acc * (uint32_t)p.BN;
+      int nkb = 1;
+      for (int kb = 0; kb < nkb; kb++) {
+        ptx::mbar_wait_a(bar_full0 + bar_off, phase);
+        if (kb == 0) nkb = *reinterpret_cast<volatile int*>(&ctl->tile_nkb[tcount & 15]);     // published before the tile's first TMA
+        ptx::tc_fence_after();
+        if (elected) {
+          const uint64_t da0 = da_base + a_off, db0 = db_base + b_off;
+#pragma unroll
+          for (int ks = 0; ks < 4; ks++)
+            ptx::mma_bf16_a<PAIR>(d_tmem, da0 + ks * a_lo, db0 + ks * b_lo, p.idesc, (uint32_t)((kb | ks) != 0));
+          if (p.ksteps == 8) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ks++)
+              ptx::mma_bf16_a<PAIR>(d_tmem, da0 + a_hi + ks * a_lo, db0 + b_hi + ks * b_lo, p.idesc, 1u);
+          }
+          ptx::mma_commit_a<PAIR>(bar_empty0 + bar_off);                                  // frees the slot (both CTAs in pair mode)
+          if (kb == nkb - 1) ptx::mma_commit_a<PAIR>(tfull0 + acc * 8);
+        }
+        __syncwarp();
+        a_off += a_stage_u; b_off += b_stage_u; bar_off += 8;
+        if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; a_off = 0; b_off = 0; bar_off = 0; }
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  } else if (warp >= 2) {
+    // =============================== epilogue ===================================
+    const int quarter = warp & 3;
+    uint32_t acc = 0, acc_phase = 0;
+    const uint32_t tfull0 = ptx::smem_u32(&ctl->tmem_full[0]), tempty0 = ptx::smem_u32(&ctl->tmem_empty[0]);
+    for (int t = t_first; t < p.num_tiles; t += t_step) {
+      float* row_ptr = nullptr;
+      long long col_stride;
+      int ncols, col0;
+      if (OP == kFprop || OP == kDgrad) {
+        const int n_tile = t % p.n_tiles, mg = t / p.n_tiles;
+        const int m_tile = PAIR ? 2 * mg + rank : mg;
+        const int qc = m_tile * 2 + (quarter >> 1);                  // this warp's 32 rows are half of one 64-image chunk
+        const int per_frame = (OP == kFprop) ? p.modules : p.W * p.H;
+        col_stride = (long long)p.N * per_frame;
+        col0 = n_tile * p.BN;
+        ncols = min(p.BN, (OP == kFprop ? p.Cout : p.Cin) - col0);
+        if (qc < p.total_chunks) {
+          const int ib = qc % p.nbc, pos = qc / p.nbc;
+          const int n = ib * 64 + (quarter & 1) * 32 + lane;
+          row_ptr = p.out + n + (long long)p.N * pos + col_stride * col0;
+        }
+      } else {
+        int tt = t;
+        const int split = tt % p.splits; tt /= p.splits;
+        const int c_tile = tt % p.n_tiles; tt /= p.n_tiles;
+        int o_tile = tt % p.m_groups; tt /= p.m_groups;
+        if (PAIR) o_tile = 2 * o_tile + rank;
+        const int o = o_tile * BM + quarter * 32 + lane;
+        col0 = c_tile * p.BN;
+        col_stride = (long long)p.Cout * p.taps;
+        ncols = min(p.BN, p.Cin - col0);
+        if (o < p.Cout) row_ptr = p.out + (long long)split * p.Cout * p.taps * p.Cin + o + (long long)p.Cout * tt + col_stride * col0;
+      }
+      ptx::mbar_wait_a(tfull0 + acc * 8, acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)p.BN;
+      for (int j0 = 0; j0 < ncols; j0 += 32) {                       // ncols is a multiple of 32 (host)
+        float v[32];
+        ptx::tmem_ld_32x32(t_addr + j0, v);
+        ptx::tmem_ld_wait();
+        if (row_ptr == nullptr) continue;
+        float* dst = row_ptr + col_stride * j0;
+        __nv_bfloat16* dst16 = p.out16 ? p.out16 + (dst - p.out) : nullptr;
+        if (OP == kFprop) {
+          float bv[32];
+          const float* bp = p.bias ? p.bias + col0 + j0 : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j++) bv[j] = bp ? __ldg(bp + j) : 0.f;
+          const bool relu = p.relu != 0;
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            float r = fmaf(p.so, v[j], bv[j]);
+            r = relu ? fmaxf(r, 0.f) : r;
+            *dst = r;
+            if (dst16) { *dst16 = __float2bfloat16_rn(r); dst16 += col_stride; }
+            dst += col_stride;
+          }
+        } else if (OP == kDgrad) {
+          float mk[32];
+          const float* mp = p.mask ? p.mask + (dst - p.out) : nullptr;
+#pragma unroll
+          for (int j = 0; j < 32; j++) { mk[j] = mp ? __ldg(mp) : 1.f; if (mp) mp += col_stride; }
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const float r = mk[j] > 0.f ? p.so * v[j] : 0.f;
+            *dst = r;
+            if (dst16) { *dst16 = __float2bfloat16_rn(r); dst16 += col_stride; }
+            dst += col_stride;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; j++) { *dst = p.so * v[j]; dst += col_stride; }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) {
+        if (rank == 0) ptx::mbar_arrive_a(tempty0 + acc * 8);
+        else ptx::mbar_arrive_remote_a(tempty0 + acc * 8, 0);
+      }
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+  }
+
+  ptx::tc_fence_before();
+  if constexpr (PAIR) ptx::cluster_sync(); else __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    if constexpr (PAIR) ptx::tmem_dealloc_2sm(tmem_base, (uint32_t)p.tmem_cols);
     else ptx::tmem_dealloc(tmem_base, (uint32_t)p.tmem_cols);
   }
 }
@@ -723,6 +1075,64 @@ void apply_pair(TcParams& p, int op, int half_granule, long long outer) {
   p.idesc = (p.idesc & ~(0x1Fu << 24)) | ((uint32_t)(2 * BM >> 4) << 24);   // M = 256
 }
 
+
+// ---- fast kernels: eligibility, stage shape, launch ------------------------------------------------------------
+bool fast_enabled() {
+  static const bool off = getenv("CONVNET_B200_NO_FAST") && getenv("CONVNET_B200_NO_FAST")[0] == '1';
+  return !off;
+}
+size_t fast_smem_bytes(size_t a_stage, size_t b_stage, int stages) {
+  return 1024 + (size_t)stages * (a_stage + b_stage) + sizeof(SmemCtl) + 16;
+}
+// K per stage: 128 elements (ksteps 8) when at least three such stages fit, else 64; b_rows_per_kstep4 = 128-byte rows of B
+// per 64 K elements.  Returns false if not even two 64-deep stages fit.
+bool fast_pick_stages(TcParams& p, int b_rows_per_kstep4) {
+  static const int force = getenv("CONVNET_B200_FAST_KSTEPS") ? atoi(getenv("CONVNET_B200_FAST_KSTEPS")) : 0;
+  for (int ksteps : {8, 4}) {
+    if (force && ksteps != force) continue;
+    const size_t a = (size_t)4096 * ksteps, b = (size_t)b_rows_per_kstep4 * (ksteps / 4) * 128;
+    int stages = kMaxStages;
+    while (stages > 1 && fast_smem_bytes(a, b, stages) > 225 * 1024) stages--;
+    if (stages >= (ksteps == 8 && !force ? 3 : 2)) {
+      p.ksteps = ksteps; p.a_stage_bytes = (uint32_t)a; p.b_rows = (int)(b / 128); p.b_tx_bytes = (uint32_t)b; p.stages = stages;
+      return true;
+    }
+  }
+  return false;
+}
+template <int OP>
+void launch_fast(const CUtensorMap& a, const CUtensorMap& b, TcParams& p) {
+  p.tmem_cols = tmem_cols_for(p.BN);
+  const size_t smem = fast_smem_bytes(p.a_stage_bytes, (size_t)p.b_rows * 128, p.stages);
+  static unsigned long long attr_devices = 0;
+  const int dev = current_device();
+  if (dev >= 64 || !((attr_devices >> dev) & 1ULL)) {
+    CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_fast_kernel<OP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (OP != kDgrad)
+      CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_fast_kernel<OP, OP != kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (dev < 64) attr_devices |= 1ULL << dev;
+  }
+  if (p.cta2) {
+    if constexpr (OP != kDgrad) {
+      cudaLaunchConfig_t cfg = {};
+      cfg.gridDim = dim3(2u * (unsigned)std::min(p.num_tiles, num_sms() / 2));
+      cfg.blockDim = dim3(kThreads);
+      cfg.dynamicSmemBytes = smem;
+      cfg.stream = state().stream;
+      cudaLaunchAttribute attr[1];
+      attr[0].id = cudaLaunchAttributeClusterDimension;
+      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+      cfg.attrs = attr; cfg.numAttrs = 1;
+      CNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_fast_kernel<OP, OP != kDgrad>, a, b, p));
+    }
+  } else {
+    const int grid = std::min(p.num_tiles, num_sms());
+    tc_fast_kernel<OP, false><<<grid, kThreads, smem, state().stream>>>(a, b, p);
+  }
+  count_launch();
+  CNB_LAUNCH_CHECK("tc_fast");
+}
+
 bool tc_enabled() {
   static int en = -1;
   if (en < 0) { const char* e = getenv("CONVNET_B200_DISABLE_TC"); en = (e && e[0] == '1') ? 0 : 1; }
@@ -746,7 +1156,7 @@ void fill_common(TcParams& p, const ConvGeom& g, const Elem& e) {
   p.cta2 = 0; p.m_groups = 0;
   static const int dbg = getenv("CONVNET_B200_TC_DEBUG") ? atoi(getenv("CONVNET_B200_TC_DEBUG")) : 0;
   p.dbg = dbg;
-  p.bias = nullptr; p.relu = 0; p.mask = nullptr;
+  p.bias = nullptr; p.relu = 0; p.mask = nullptr; p.out16 = nullptr;
   p.out_frame_step = g.out_frame_step;
   p.total_chunks = 0;
 }
@@ -898,6 +1308,9 @@ static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float*
     ws = (uint8_t*)workspace(part_bytes);
   }
   if (p.splits > 1) { p.out = (float*)ws; p.bias = nullptr; p.relu = 0; }   // partial sums; the epilogue moves to reduce_split
+  // bf16 twin of the output from the same registers: only when this launch writes the final value of EVERY element
+  const bool emit = fuse.out16 != nullptr && p.splits == 1 && g.cout0 == 0 && g.Cout == g.CoutT;
+  if (emit) p.out16 = fuse.out16;
   p.a_merged = (allow_merge() && g.frames == 1 && g.N % 128 == 0) ? 1 : 0;
   p.b_merged = (allow_merge() && g.Cout % e.chunk == 0 && bn_local % e.chunk == 0) ? 1 : 0;
   // frames of a 3-D conv start in_frame_step floats apart and see Cin (= Cin3d*kt) channels
@@ -938,7 +1351,33 @@ static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float*
       if (!make_map(&mb, flt, e, 3, dims, str, box, true)) return false;
     }
   }
-  launch<kFprop>(ma, mb, p);
+  bool done = false;
+  // the lean kernel takes the shapes the training step lives in (see tc_fast_kernel); the rest stays on the general one
+  if (bf && fast_enabled() && !x_mode && p.a_merged && p.splits == 1 && st == 0.f && g.Cout % 32 == 0 && p.BN % 32 == 0) {
+    TcParams f = p;
+    f.b_chunks = ceil_div(bn_local, 64);
+    f.b_merged = (g.Cout % 64 == 0 && bn_local % 64 == 0 && p.BN % 64 == 0) ? 1 : 0;
+    if (fast_pick_stages(f, f.b_chunks * 64)) {
+      Elem e2 = e; e2.bk = f.ksteps * 16;
+      f.kc_blocks = ceil_div(g.Cin, e2.bk);
+      CUtensorMap fa, fb;
+      bool ok = merged_image_map(&fa, img, e2, g, g.W, g.H, g.Cin, false);
+      if (ok && f.b_merged) {
+        const long long dims[4] = {64, g.Cin, g.Cout / 64, taps};
+        const long long str[3] = {(long long)g.Cout * taps, 64, g.Cout};
+        const int box[4] = {64, e2.bk, f.b_chunks, 1};
+        ok = make_map(&fb, flt, e2, 4, dims, str, box, true);
+      } else if (ok) {
+        const long long dims[3] = {g.Cout, taps, g.Cin};
+        const long long str[2] = {g.Cout, (long long)g.Cout * taps};
+        const int box[3] = {64, 1, e2.bk};
+        ok = make_map(&fb, flt, e2, 3, dims, str, box, true);
+      }
+      if (ok) { launch_fast<kFprop>(fa, fb, f); done = true; }
+    }
+  }
+  if (!done) launch<kFprop>(ma, mb, p);
+  if (emit && fuse.emitted) *fuse.emitted = true;
   if (p.splits > 1) reduce_split((const float*)ws, out, out_elems, p.splits, st, so, bias, (long long)g.modules * g.N, fuse.relu, nullptr);
   state().last_conv_path = bf ? kPathTcBf16 : kPathTcTf32;
   return true;
@@ -1015,7 +1454,19 @@ static bool tc_conv_down_impl(const ConvGeom& g, const float* derivs, const floa
     reduce_split((const float*)ws, out, out_elems, p.splits, st, so, nullptr, 1, 0, fuse.relu_mask);
   } else if (whole) {
     p.st = st; p.out = out; p.mask = fuse.relu_mask ? fuse.relu_mask + (long long)g.cin0 * g.H * g.W * g.N : nullptr;
-    launch<kDgrad>(ma, mb, p);
+    p.out16 = fuse.out16;                              // `whole`: every element gets its final value here
+    bool done = false;
+    if (bf && fast_enabled() && p.a_merged && !p.cta2 && st == 0.f && g.Cin % 32 == 0 && p.BN % 32 == 0 && g.Cout % 8 == 0) {
+      TcParams f = p;
+      if (fast_pick_stages(f, bn_local)) {
+        Elem e2 = e; e2.bk = f.ksteps * 16;
+        f.kc_blocks = ceil_div(g.Cout, e2.bk);
+        CUtensorMap fa;
+        if (merged_image_map(&fa, der, e2, g, g.modX, g.modY, g.Cout, false)) { launch_fast<kDgrad>(fa, mb, f); done = true; }
+      }
+    }
+    if (!done) launch<kDgrad>(ma, mb, p);
+    if (fuse.out16 && fuse.emitted) *fuse.emitted = true;
   } else {
     // the reference scales the WHOLE target first (gemm.cu:760, conv3d_gemm.cu:98); frame windows overlap,
     // so frames are accumulated by stream-ordered launches
@@ -1097,15 +1548,28 @@ static bool tc_conv_outp_impl(const ConvGeom& g, const float* images, const floa
     const int box[5] = {32, 8, g.ky, 1, 1};                   // 8 x-taps x ky rows of one channel: ky*8 GEMM columns
     if (!make_map(&mb, img, e, 5, dims, str, box, false)) return false;
   } else if (!image_map(&mb, img, e, g, g.W, g.H, g.Cin, g.in_frame_step, false, bn_local)) return false;
-  if (p.splits == 1) {
-    p.out = targets;
-    launch<kWgrad>(ma, mb, p);
-  } else {
-    float* part = (float*)ws;
-    p.out = part;
-    launch<kWgrad>(ma, mb, p);
-    reduce_partials(part, targets, elems, 1, p.splits, st, so);
+  p.out = p.splits == 1 ? targets : (float*)ws;
+  bool done = false;
+  if (bf && fast_enabled() && !x_mode && g.frames == 1 && g.N % 128 == 0 && g.Cin % 32 == 0 && p.BN % 32 == 0 &&
+      (p.splits > 1 || st == 0.f)) {
+    TcParams f = p;
+    if (p.splits > 1) f.so = 1.f;                      // partial sums are scaled by reduce_partials
+    if (fast_pick_stages(f, bn_local)) {
+      const long long N = g.N, cps = f.ksteps / 4;
+      // (n_lo = 64, x, y, channel, n_hi = N/64) views: one request brings `cps` 64-image panels of a module
+      const long long adims[5] = {64, g.modX, g.modY, g.Cout, N / 64}, astr[4] = {N, N * g.modX, N * g.modX * g.modY, 64};
+      const int abox[5] = {64, 1, 1, BM, (int)cps};
+      const long long bdims[5] = {64, g.W, g.H, g.Cin, N / 64}, bstr[4] = {N, N * g.W, N * g.W * g.H, 64};
+      const int bbox[5] = {64, 1, 1, bn_local, (int)cps};
+      CUtensorMap fa, fb;
+      if (make_map(&fa, der, e, 5, adims, astr, abox, false) && make_map(&fb, img, e, 5, bdims, bstr, bbox, false)) {
+        launch_fast<kWgrad>(fa, fb, f);
+        done = true;
+      }
+    }
   }
+  if (!done) launch<kWgrad>(ma, mb, p);
+  if (p.splits > 1) reduce_partials((const float*)ws, targets, elems, 1, p.splits, st, so);
   state().last_conv_path = bf ? kPathTcBf16 : kPathTcTf32;
   return true;
 }

@@ -56,7 +56,8 @@ int num_sms() {
     CNB_CUDA_CHECK(cudaDeviceGetAttribute(&s.num_sms, cudaDevAttrMultiProcessorCount, dev));
     s.sm_device = dev;
   }
-  return s.num_sms;
+  const int usable = s.num_sms - s.sm_reserve;
+  return usable >= 8 ? usable : (s.num_sms < 8 ? s.num_sms : 8);
 }
 
 }  // namespace cnb
@@ -78,6 +79,7 @@ void convnet_b200_fuse_next(const float* bias, int relu, const float* relu_mask)
   state().fuse.bias = bias; state().fuse.relu = relu; state().fuse.relu_mask = relu_mask;
 }
 void convnet_b200_emit_bf16_next(void) { state().fuse.emit_bf16 = 1; }
+void convnet_b200_reserve_sms(int n) { state().sm_reserve = n > 0 ? n : 0; }
 void convnet_b200_bf16_stage(const float* ptr, long long n) { bf16_stage(ptr, n); }
 void convnet_b200_bf16_ensure(const float* ptr, long long n) { bf16_ensure(ptr, n); }
 int convnet_b200_bf16_is_staged(const float* ptr, long long n) { return want_bf16() && bf16_staged(ptr, n) != nullptr; }

@@ -142,6 +142,15 @@ bool DataParallelSync::Init(int rank, int world, const char idbytes[128]) {
   rank_ = rank; world_ = world;
   ncclUniqueId id;
   memcpy(&id, idbytes, 128);
+  // the collective's CTAs run beside persistent conv kernels that own every SM they touch: keep NCCL narrow and let the
+  // conv grids leave exactly that many SMs free while a collective is in flight (convnet_b200_reserve_sms)
+  const char* e = getenv("CONVNET_B200_NCCL_CTAS");
+  nccl_ctas_ = e ? atoi(e) : 8;
+  if (nccl_ctas_ > 0 && !getenv("NCCL_MAX_CTAS")) {
+    char buf[16]; snprintf(buf, sizeof(buf), "%d", nccl_ctas_);
+    setenv("NCCL_MAX_CTAS", buf, 1);
+  }
+  if (nccl_ctas_ < 0) nccl_ctas_ = 0;
   ncclComm_t c;
   NCCL_CHECK(nccl().CommInitRank(&c, world, id, rank));
   comm_ = c;
@@ -155,21 +164,14 @@ void DataParallelSync::Broadcast(float* buf, size_t count) {
   HOST_CUDA_CHECK(cudaEventRecord(ready_, Matrix::Stream()));
   HOST_CUDA_CHECK(cudaStreamWaitEvent(comm_stream_, ready_, 0));
   NCCL_CHECK(nccl().Bcast(buf, buf, count, ncclFloat, 0, (ncclComm_t)comm_, comm_stream_));
-  pending_ = true;
-  WaitAll();
-}
-void DataParallelSync::AllReduceAverageAsync(float* buf, size_t offset, size_t count) {
-  if (world_ <= 1 || count == 0) return;
-  HOST_CUDA_CHECK(cudaEventRecord(ready_, Matrix::Stream()));          // gradients of this bucket are final
-  HOST_CUDA_CHECK(cudaStreamWaitEvent(comm_stream_, ready_, 0));
-  NCCL_CHECK(nccl().AllReduce(buf + offset, buf + offset, count, ncclFloat, ncclAvg, (ncclComm_t)comm_, comm_stream_));
-  pending_ = true;
-}
-void DataParallelSync::WaitAll() {
-  if (!pending_) return;
   HOST_CUDA_CHECK(cudaEventRecord(done_, comm_stream_));
   HOST_CUDA_CHECK(cudaStreamWaitEvent(Matrix::Stream(), done_, 0));
-  pending_ = false;
+}
+void DataParallelSync::AllReduceAverageAsync(float* buf, size_t offset, size_t count, cudaStream_t side) {
+  if (world_ <= 1 || count == 0) return;
+  HOST_CUDA_CHECK(cudaEventRecord(ready_, Matrix::Stream()));          // gradients of this bucket are final
+  HOST_CUDA_CHECK(cudaStreamWaitEvent(side, ready_, 0));
+  NCCL_CHECK(nccl().AllReduce(buf + offset, buf + offset, count, ncclFloat, ncclAvg, (ncclComm_t)comm_, side));
 }
 
 // =================================================================== ConvNet
@@ -219,6 +221,10 @@ ConvNet::ConvNet(const ModelConfig& model, int batch_size) : model_(model), batc
 void ConvNet::InvalidateStaging() { convnet_b200_bf16_invalidate(nullptr); }
 
 ConvNet::~ConvNet() {
+  if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); }
+  if (ev_main_) cudaEventDestroy(ev_main_);
+  if (ev_side_) cudaEventDestroy(ev_side_);
+  convnet_b200_reserve_sms(0);
   convnet_b200_bf16_invalidate(nullptr);                     // the buffers go away; a later net may get the same addresses
   for (Edge* e : edges_) delete e;
   for (Layer* l : layers_) delete l;
@@ -253,6 +259,10 @@ void ConvNet::AllocateMemory() {
   }
   HOST_CUDA_CHECK(cudaStreamSynchronize(Matrix::Stream()));
   InvalidateStaging();
+  HOST_CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+  HOST_CUDA_CHECK(cudaEventCreateWithFlags(&ev_main_, cudaEventDisableTiming));
+  HOST_CUDA_CHECK(cudaEventCreateWithFlags(&ev_side_, cudaEventDisableTiming));
+  SetBucketFloats((size_t)8 << 20);
 }
 
 void ConvNet::Fprop(bool train) {                            // convnet.cc:377-388
@@ -297,20 +307,52 @@ void ConvNet::Bprop() {                                      // convnet.cc:390-4
       out->ApplyDerivativeOfActivation(want_out && act_pass);
     }
     e->ComputeOuter(in->GetState(), out->GetDeriv());
+    // data parallel: ship every bucket whose last gradient just became final (side stream, overlaps the rest of bprop)
+    if (dp_ && dp_->world() > 1)
+      for (const Bucket& b : buckets_)
+        if (b.trigger == i - 1) {
+          if (!side_pending_) convnet_b200_reserve_sms(dp_->reserved_sms());
+          dp_->AllReduceAverageAsync(grad_parameters_.GetDevData(), b.lo, b.hi - b.lo, side_);
+          side_pending_ = true;
+        }
     if (!in->IsInput()) {
       const bool want_in = bf16 && i >= 2 && edges_[i - 2]->WantsBf16Deriv();
       e->SetEmitDown(want_in && !in->HasDropout() && !in->HasSeparateDerivPass());
       e->ComputeDown(out->GetDeriv(), in->GetState(), out->GetState(), in->GetDeriv(), /*overwrite=*/true);
     }
-    // data-parallel: ship every bucket whose last gradient just became final (side stream, overlaps the rest of bprop)
-    if (dp_ && dp_->world() > 1)
+    // the optimizer step of a bucket follows its all-reduce on the side stream once its edges are done with the weights
+    if (eager_update_)
       for (const Bucket& b : buckets_)
-        if (b.trigger == i - 1) dp_->AllReduceAverageAsync(grad_parameters_.GetDevData(), b.lo, b.hi - b.lo);
+        if (b.trigger == i - 1) IssueBucketUpdate(b);
   }
 }
 
+// the SGD step of one bucket on the side stream, after (stream order) that bucket's all-reduce and after (event) the
+// compute stream has finished reading the bucket's weights in this step
+void ConvNet::IssueBucketUpdate(const Bucket& b) {
+  std::vector<CnbSgdTensor> tensors;
+  for (int i = b.trigger; i <= b.last; i++)
+    if (EdgeWithWeight* w = dynamic_cast<EdgeWithWeight*>(edges_[i])) w->AppendSgdTensors(tensors);
+  if (tensors.empty()) return;
+  HOST_CUDA_CHECK(cudaEventRecord(ev_main_, Matrix::Stream()));
+  HOST_CUDA_CHECK(cudaStreamWaitEvent(side_, ev_main_, 0));
+  void* main_stream = convnet_b200_get_stream();
+  convnet_b200_set_stream(side_);
+  cnb_sgd_momentum_multi(tensors.data(), (int)tensors.size());
+  convnet_b200_set_stream(main_stream);
+  side_pending_ = true;
+}
+void ConvNet::WaitSide() {
+  if (!side_pending_) return;
+  HOST_CUDA_CHECK(cudaEventRecord(ev_side_, side_));
+  HOST_CUDA_CHECK(cudaStreamWaitEvent(Matrix::Stream(), ev_side_, 0));
+  side_pending_ = false;
+  convnet_b200_reserve_sms(0);
+}
+
 void ConvNet::UpdateWeights() {                              // convnet.cc:440-450
-  if (dp_) dp_->WaitAll();                                   // replaces Accumulate + Broadcast (MPI through host memory)
+  WaitSide();                                                // replaces Accumulate + Broadcast (MPI through host memory)
+  if (updated_in_bprop_) { updated_in_bprop_ = false; return; }        // TrainOneBatch: every bucket was updated on the side stream
   // one multi-tensor SGD launch for every weight and bias matrix of the net (the reference loops edges: optimizer.cc:174-200)
   std::vector<CnbSgdTensor> tensors;
   for (Edge* e : edges_)
@@ -324,7 +366,11 @@ void ConvNet::TrainOneBatch(float* loss_out) {               // convnet.cc:475-4
   if (loss_out) {                                            // GetLoss: one scalar D2H per step, like the reference
     cnb_sum(OutputLayer().GetLossPerImage(), loss_sum_.GetDevData(), batch_size_);
   }
+  static const bool no_eager = getenv("CONVNET_B200_NO_EAGER_UPDATE") && getenv("CONVNET_B200_NO_EAGER_UPDATE")[0] == '1';
+  eager_update_ = !no_eager;
   Bprop();
+  updated_in_bprop_ = eager_update_;
+  eager_update_ = false;
   UpdateWeights();
   if (loss_out) *loss_out = loss_sum_.ReadValue(0);
   step_++;
@@ -333,18 +379,21 @@ void ConvNet::TrainOneBatch(float* loss_out) {               // convnet.cc:475-4
 std::vector<Bucket> PlanBuckets(const std::vector<size_t>& edge_offset, const std::vector<size_t>& edge_size,
                                 size_t bucket_floats) {
   std::vector<Bucket> out;
+  int first_weighted = -1;
+  for (int i = 0; i < (int)edge_size.size(); i++) if (edge_size[i] != 0) { first_weighted = i; break; }
   size_t lo = 0, hi = 0;
   bool open = false;
-  int last_weighted = -1;
+  int last_weighted = -1, top = -1;
   for (int i = (int)edge_size.size() - 1; i >= 0; i--) {
     if (edge_size[i] == 0) continue;
     const size_t e_lo = edge_offset[i], e_hi = e_lo + DIVUP(edge_size[i], (size_t)128) * 128;
-    if (!open) { hi = e_hi; open = true; }
+    if (open && i == first_weighted) { out.push_back({lo, hi, last_weighted, top}); open = false; }   // the first edge travels alone
+    if (!open) { hi = e_hi; open = true; top = i; }
     lo = e_lo;
     last_weighted = i;
-    if (hi - lo >= bucket_floats) { out.push_back({lo, hi, i}); open = false; }
+    if (hi - lo >= bucket_floats) { out.push_back({lo, hi, i, top}); open = false; }
   }
-  if (open) out.push_back({lo, hi, last_weighted});
+  if (open) out.push_back({lo, hi, last_weighted, top});
   return out;
 }
 
@@ -354,6 +403,7 @@ void ConvNet::SetDataParallel(DataParallelSync* dp, size_t bucket_floats) {
                   ((unsigned long long)((dp ? dp->rank() : 0) + 1) * 0xD1B54A32D192ED03ULL);
   buckets_ = PlanBuckets(edge_offset_, edge_size_, bucket_floats);
 }
+void ConvNet::SetBucketFloats(size_t bucket_floats) { buckets_ = PlanBuckets(edge_offset_, edge_size_, bucket_floats); }
 void ConvNet::BroadcastParameters() {
   if (dp_) dp_->Broadcast(parameters_.GetDevData(), parameters_.GetNumEls());
   InvalidateStaging();

@@ -82,22 +82,23 @@ class DataParallelSync {
   int world() const { return world_; }
   int rank() const { return rank_; }
   void Broadcast(float* buf, size_t count);                     // initial parameters from rank 0 (convnet.cc:300-309)
-  // average buf[offset, offset+count) over ranks, ordered after everything already on the compute stream
-  void AllReduceAverageAsync(float* buf, size_t offset, size_t count);
-  void WaitAll();                                               // compute stream waits for every pending all-reduce
+  // average buf[offset, offset+count) over ranks on `side`, ordered after everything already on the compute stream
+  void AllReduceAverageAsync(float* buf, size_t offset, size_t count, cudaStream_t side);
+  int reserved_sms() const { return nccl_ctas_; }               // SMs the collective's CTAs need while it is in flight
  private:
   void* comm_ = nullptr;
-  cudaStream_t comm_stream_ = nullptr;
+  cudaStream_t comm_stream_ = nullptr;                          // broadcast only; the all-reduces ride on ConvNet's side stream
   cudaEvent_t ready_ = nullptr, done_ = nullptr;
-  int rank_ = 0, world_ = 1;
-  bool pending_ = false;
+  int rank_ = 0, world_ = 1, nccl_ctas_ = 0;
 };
 
-// Gradient buckets for the overlapped all-reduce.  Back-propagation finalises edge gradients from the LAST
-// edge to the first, and edge slices are adjacent in the flat buffer (128-float padded), so a bucket is the
-// contiguous range [lo, hi) that becomes final when edge `trigger` has run ComputeOuter.  Buckets are closed
-// once they hold >= bucket_floats; every parameter belongs to exactly one bucket.
-struct Bucket { size_t lo, hi; int trigger; };
+// Gradient buckets: the unit of the overlapped all-reduce AND of the optimizer step.  Back-propagation finalises edge
+// gradients from the LAST edge to the first, and edge slices are adjacent in the flat buffer (128-float padded), so a
+// bucket is the contiguous range [lo, hi) — the edges [trigger, last] — that becomes final when edge `trigger` has run
+// ComputeOuter.  Buckets are closed once they hold >= bucket_floats; the FIRST weighted edge of the net always gets a
+// bucket of its own (its gradient is the last to appear: only that small exchange stays exposed at the end of the step);
+// every parameter belongs to exactly one bucket.
+struct Bucket { size_t lo, hi; int trigger, last; };
 std::vector<Bucket> PlanBuckets(const std::vector<size_t>& edge_offset, const std::vector<size_t>& edge_size,
                                 size_t bucket_floats);
 
@@ -113,6 +114,7 @@ class ConvNet {
   void TrainOneBatch(float* loss_out);                          // convnet.cc:475-485
   float GetLoss();                                              // sum of per-image CE (synchronises)
   void SetDataParallel(DataParallelSync* dp, size_t bucket_floats);
+  void SetBucketFloats(size_t bucket_floats);                   // re-plan the buckets (also used without data parallelism)
   void BroadcastParameters();
   void InvalidateStaging();                                     // after any write to the parameters from outside UpdateWeights
 
@@ -138,8 +140,16 @@ class ConvNet {
   Matrix parameters_, grad_parameters_, history_, loss_sum_;
   std::vector<size_t> edge_offset_, edge_size_;
   size_t num_params_ = 0;
+  // Side-stream pipeline of TrainOneBatch: as soon as a bucket's gradients are final its all-reduce (data parallel) is
+  // enqueued on side_, and once the bucket's edges have finished their dgrad the multi-tensor SGD step of that bucket
+  // follows on the same stream — the exchange and the update of the FC layers hide under the conv back-propagation.
+  void IssueBucketUpdate(const Bucket& b);
+  void WaitSide();
   DataParallelSync* dp_ = nullptr;
   std::vector<Bucket> buckets_;
+  cudaStream_t side_ = nullptr;
+  cudaEvent_t ev_main_ = nullptr, ev_side_ = nullptr;
+  bool eager_update_ = false, side_pending_ = false, updated_in_bprop_ = false;
   unsigned long long step_ = 0;
   unsigned long long dropout_salt_ = 0xD1B54A32D192ED03ULL;      // model seed and data-parallel rank, see SetDataParallel
 };

@@ -42,6 +42,13 @@ int convnet_b200_last_conv_path(void);
 unsigned long long convnet_b200_launch_count(void);
 void convnet_b200_reset_launch_count(void);
 
+/* The conv kernels are persistent: one CTA (or CTA pair) per SM, each owning most of the SM's shared memory.  A kernel
+ * of another library that must run CONCURRENTLY (an NCCL collective on a side stream) cannot co-reside with them and
+ * would otherwise wait for — or push out — a whole wave.  convnet_b200_reserve_sms(n) makes the persistent grids leave
+ * n SMs free until it is called again with 0.  (host/convnet.cc reserves the SMs of the gradient all-reduce while it
+ * is in flight.) */
+void convnet_b200_reserve_sms(int n);
+
 /* Free cached device scratch (wgrad / split-K partial sums, bf16 staging buffers).  Never required. */
 void convnet_b200_release_workspace(void);
 

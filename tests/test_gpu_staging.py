@@ -1,0 +1,75 @@
+"""bf16 staging coherence (csrc/stage.cu): copies written by the producing kernels, invalidation by library writes,
+and the CONVNET_B200_STAGE_VERIFY debug mode that catches a stale copy."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+pytestmark = pytest.mark.gpu
+
+
+def _run(*args):
+    env = dict(os.environ, CONVNET_B200_STAGE_VERIFY="1")
+    return subprocess.run([sys.executable, os.path.join(ROOT, "tests", "staging_worker.py"), *args],
+                          capture_output=True, text=True, timeout=900, env=env)
+
+
+@pytest.mark.parametrize("model,batch,steps", [("tiny", 32, 3), ("alexnet", 32, 2)])
+def test_emitted_copies_equal_a_fresh_conversion(model, batch, steps):
+    r = _run("train", model, str(batch), str(steps))
+    assert r.returncode == 0 and "VERIFY-TRAIN-OK" in r.stdout, (r.returncode, r.stdout[-1500:], r.stderr[-1500:])
+
+
+def test_stale_copy_is_detected_in_verify_mode():
+    r = _run("stale")
+    assert "FIRST-USE-OK" in r.stdout and "NOT-DETECTED" not in r.stdout
+    assert r.returncode != 0 and "STAGE_VERIFY" in r.stderr, (r.returncode, r.stdout, r.stderr[-1500:])
+
+
+def test_library_writes_keep_copies_coherent():
+    import torch
+    from convnet_b200 import conv_gemm as cg
+    from convnet_b200 import lib
+    from convnet_b200.abi import GetConvDesc
+    from convnet_b200.matrix import CUDAMatrix
+    L = lib.load()
+    lib.set_precision("bf16")
+    try:
+        N, W, Cin, Cout = 128, 8, 64, 64
+        d = GetConvDesc(Cin, Cout, 3, 3, 1, 1, 1, 1)
+        x = CUDAMatrix(N, W * W * Cin, (N, W, W, Cin)); x.storage.normal_()
+        w = CUDAMatrix(Cout, 9 * Cin, (Cout, 3, 3, Cin)); w.storage.normal_().mul_(0.05)
+        y = CUDAMatrix(N, W * W * Cout, (N, W, W, Cout))
+        n = x.storage.numel()
+        staged = lambda m: L.convnet_b200_bf16_is_staged(m.ptr, m.storage.numel())
+        L.convnet_b200_bf16_stage(x.ptr, n)
+        assert staged(x) == 1
+        L.cnb_relu(x.ptr, n)                                   # a library write without an emit request: the copy is dropped
+        assert staged(x) == 0
+        L.convnet_b200_emit_bf16_next(); L.cnb_relu(x.ptr, n)  # with the request: a fresh copy from the same kernel
+        assert staged(x) == 1
+        # conv output: requested -> staged, and the copy equals a conversion of the fp32 output
+        L.convnet_b200_emit_bf16_next(); cg.convUp(x, w, y, d)
+        assert lib.last_conv_path() == "tcgen05-bf16" and staged(y) == 1
+        y2 = CUDAMatrix(N, W * W * Cout, (N, W, W, Cout)); cg.convUp(x, w, y2, d)
+        assert staged(y2) == 0
+        # consumer results with the emitted copy == results with an explicit conversion
+        w2 = CUDAMatrix(Cout, 9 * Cout, (Cout, 3, 3, Cout)); w2.storage.normal_().mul_(0.05)
+        z1 = CUDAMatrix(N, W * W * Cout, (N, W, W, Cout)); cg.convUp(y, w2, z1, d)
+        z2 = CUDAMatrix(N, W * W * Cout, (N, W, W, Cout)); cg.convUp(y2, w2, z2, d)
+        assert torch.equal(z1.storage, z2.storage)
+        # the SGD kernel refreshes the staged copy of the weights it updates
+        L.convnet_b200_bf16_stage(w.ptr, w.storage.numel())
+        h, g_ = torch.zeros_like(w.storage), torch.randn_like(w.storage)
+        L.cnb_sgd_momentum(w.ptr, h.data_ptr(), g_.data_ptr(), w.storage.numel(), 0.01, 0.9, 5e-4)
+        assert staged(w) == 1
+        z3 = CUDAMatrix(N, W * W * Cout, (N, W, W, Cout)); cg.convUp(x, w, z3, d)          # refreshed copy
+        L.convnet_b200_bf16_invalidate(w.ptr)
+        z4 = CUDAMatrix(N, W * W * Cout, (N, W, W, Cout)); cg.convUp(x, w, z4, d)          # converted inside the call
+        assert torch.equal(z3.storage, z4.storage)
+    finally:
+        L.convnet_b200_bf16_invalidate(None)
+        lib.set_precision("fp32")
