@@ -27,9 +27,18 @@ struct Emit {
   void finish() { if (buf && !done) bf16_stage(target, n); }     // nobody filled it: one conversion pass (re-validates the slot)
 };
 
+// bias gradient requested with the write (convnet_b200_fuse_next_bias_grad): finish from the kernel's per-slice sums, or
+// run the column-sum pass when the kernel did not produce them.  rows = images x positions, cols = channels.
+void finish_bias_grad(const Fuse& fuse, const float* part, int slices, const float* target, long long rows, int cols) {
+  if (!fuse.bias_grad) return;
+  if (slices > 0) colsum_finish(part, fuse.bias_grad, cols, slices, fuse.bg_st, fuse.bg_so);
+  else cnb_channel_bias_grad(target, fuse.bias_grad, rows, cols, fuse.bg_st, fuse.bg_so);
+}
+
 void conv_up(const ConvGeom& g, const float* images, const float* filters, float* targets, float st, float so) {
   Fuse fuse = take_fuse();
   if (!g.conv && fuse.any()) { fprintf(stderr, "convnet_b200: epilogue fusion is not available for untied filters\n"); abort(); }
+  CNB_REQUIRE(!fuse.bias_grad, "convUp: a fused bias gradient belongs to a backward call");
   Emit emit(targets, g.out_total, fuse.emit_bf16 != 0);
   emit.attach(fuse);
   if (!(state().precision != kPrecFP32 && tc_conv_up(g, images, filters, targets, st, so, fuse))) {
@@ -55,6 +64,8 @@ void conv_down(const ConvGeom& g, const float* derivs, const float* filters, flo
     const long long n4 = g.img_total;             // (cnb_relu_deriv would consume a pending fuse request; none is pending here)
     cnb_relu_deriv(targets, late_mask, n4);
   }
+  CNB_REQUIRE(!fuse.bias_grad || g.frames == 1, "convDown: fused bias gradient is 2-D only");
+  finish_bias_grad(fuse, nullptr, 0, targets, (long long)g.N * g.W * g.H, g.CinT);
   emit.finish();
 }
 
@@ -113,8 +124,11 @@ void do_max_undo(const char* what, cudamat* images, cudamat* maxGrads, cudamat* 
   CNB_REQUIRE(maxActs->size[0] == g.N && maxActs->size[1] == maxGrads->size[1], what);
   const Fuse fuse = take_fuse();
   Emit emit(targets->data_device, (long long)targets->size[0] * targets->size[1], fuse.emit_bf16 != 0);
+  int slices = 0;
+  float* part = fuse.bias_grad ? (float*)workspace(sizeof(float) * (size_t)g.H * g.C * g.T) : nullptr;
   emit.done = max_pool_undo(g, images->data_device, maxGrads->data_device, maxActs->data_device, targets->data_device, st,
-                            1.f, fuse.relu_mask, emit.buf);
+                            1.f, fuse.relu_mask, emit.buf, g.T == 1 ? part : nullptr, &slices);
+  finish_bias_grad(fuse, part, slices, targets->data_device, (long long)g.N * g.W * g.H * g.T, g.C);
   emit.finish();
 }
 void do_avg_undo(const char* what, cudamat* avgGrads, cudamat* targets, Shape4D* gs, Shape4D* ts, ConvDesc d, float st,
@@ -122,7 +136,11 @@ void do_avg_undo(const char* what, cudamat* avgGrads, cudamat* targets, Shape4D*
   PoolGeom g = pool_geom(*ts, *gs, targets, avgGrads, d, what);
   const Fuse fuse = take_fuse();
   Emit emit(targets->data_device, (long long)targets->size[0] * targets->size[1], fuse.emit_bf16 != 0);
-  emit.done = avg_pool_undo(g, avgGrads->data_device, targets->data_device, st, so, fuse.relu_mask, emit.buf);
+  int slices = 0;
+  float* part = fuse.bias_grad ? (float*)workspace(sizeof(float) * (size_t)g.H * g.C * g.T) : nullptr;
+  emit.done = avg_pool_undo(g, avgGrads->data_device, targets->data_device, st, so, fuse.relu_mask, emit.buf,
+                            g.T == 1 ? part : nullptr, &slices);
+  finish_bias_grad(fuse, part, slices, targets->data_device, (long long)g.N * g.W * g.H * g.T, g.C);
   emit.finish();
 }
 
@@ -166,6 +184,7 @@ void do_rnorm_undo(const char* what, cudamat* outGrads, cudamat* inputs, cudamat
   CNB_REQUIRE(outGrads->size[0] == inputs->size[0] && outGrads->size[1] == inputs->size[1], what);
   const long long L = els / F / frames;
   const Fuse fuse = take_fuse();
+  CNB_REQUIRE(!fuse.bias_grad, "ResponseNormCrossMapUndo: no fused bias gradient here");
   Emit emit(targets->data_device, els, fuse.emit_bf16 != 0);
   for (int t = 0; t < frames; t++)
     rnorm_undo(outGrads->data_device + (long long)t * L * F, inputs->data_device + (long long)t * L * F,

@@ -56,6 +56,9 @@ struct Fuse {
   int relu = 0;                      // fprop: max(., 0) after the bias
   const float* relu_mask = nullptr;  // dgrad / pool undo: result zeroed where relu_mask <= 0 (same shape as the target)
   int emit_bf16 = 0;                 // any writer: also leave a staged bf16 copy of the whole target (convnet_b200_emit_bf16_next)
+  // the writer also produces the bias gradient of the edge that consumes the target as its output derivative
+  // (convnet_b200_fuse_next_bias_grad): grad_bias[c] = bg_st*grad_bias[c] + bg_so * sum over images and positions
+  float* bias_grad = nullptr; float bg_st = 0.f, bg_so = 1.f;
   // internal (filled by the ABI wrapper): where the bf16 twin of the target goes; a kernel that writes it sets *emitted
   __nv_bfloat16* out16 = nullptr;
   bool* emitted = nullptr;

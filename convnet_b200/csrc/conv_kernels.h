@@ -46,11 +46,16 @@ void end_write(float* target, long long n, bool want_emit, const __nv_bfloat16* 
 // targets_bf16 (may be null): also write the bf16 twin of the target; the return value says whether the kernel did
 bool pool_forward(const PoolGeom& g, bool is_max, const float* images, float* targets, float scaleOutput,
                   __nv_bfloat16* targets_bf16 = nullptr);
+// colsum / colsum_slices (may be null): where a kernel that can do so leaves per-slice channel sums of the tensor it wrote,
+// colsum[slice * channels + c] (*colsum_slices = number of slices, 0 = not done) — the bias gradient of the edge below
 bool max_pool_undo(const PoolGeom& g, const float* images, const float* maxGrads, const float* maxActs,
                    float* targets, float scaleTargets, float scaleOutput, const float* relu_mask,
-                   __nv_bfloat16* targets_bf16 = nullptr);
+                   __nv_bfloat16* targets_bf16 = nullptr, float* colsum = nullptr, int* colsum_slices = nullptr);
 bool avg_pool_undo(const PoolGeom& g, const float* avgGrads, float* targets, float scaleTargets,
-                   float scaleOutput, const float* relu_mask, __nv_bfloat16* targets_bf16 = nullptr);
+                   float scaleOutput, const float* relu_mask, __nv_bfloat16* targets_bf16 = nullptr,
+                   float* colsum = nullptr, int* colsum_slices = nullptr);
+// grad_bias[c] = st*grad_bias[c] + so * sum_slices part[slice*cols + c]   (elementwise.cu)
+void colsum_finish(const float* part, float* grad_bias, int cols, int slices, float st, float so);
 
 // rnorm.cu
 // relu / targets_bf16: fused epilogue (max(., 0); a bf16 copy of the output) — only when rnorm_can_fuse(numFilters)

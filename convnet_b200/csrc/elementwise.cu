@@ -234,6 +234,12 @@ __global__ void sum_kernel(const float* __restrict__ a, float* out, int n) {   /
   }
 }
 
+void colsum_finish(const float* part, float* grad_bias, int cols, int slices, float st, float so) {
+  colsum_final_kernel<<<ceil_div(cols, 128), 128, 0, state().stream>>>(part, grad_bias, cols, slices, st, so);
+  count_launch();
+  CNB_LAUNCH_CHECK("colsum_finish");
+}
+
 }  // namespace cnb
 
 using namespace cnb;

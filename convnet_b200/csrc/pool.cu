@@ -264,7 +264,8 @@ __global__ void __launch_bounds__(256) pool_undo_rows_kernel(PoolGeom g, const f
                                                               const float* __restrict__ grads,
                                                               const float* __restrict__ acts, float* targets,
                                                               float st, float so, const float* __restrict__ relu_mask,
-                                                              int nv_shift, __nv_bfloat16* __restrict__ targets16) {
+                                                              int nv_shift, __nv_bfloat16* __restrict__ targets16,
+                                                              float* __restrict__ rowsum) {
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * g.W;
   const long long in_plane = (long long)g.N * g.W * g.H * blockIdx.y, out_plane = (long long)g.N * g.modX * g.modY * blockIdx.y;
@@ -275,6 +276,7 @@ __global__ void __launch_bounds__(256) pool_undo_rows_kernel(PoolGeom g, const f
   const bool mask_is_input = MAX && relu_mask == images;     // max-pool right above the ReLU layer: mask == pool input
   float* out = targets + in_plane;
   __nv_bfloat16* out16 = targets16 ? targets16 + in_plane : nullptr;
+  float total = 0.f;                            // rowsum: sum of everything this thread stores (bias gradient of the edge below)
   for (int Y = blockIdx.x; Y < g.H; Y += gridDim.x) {
     int y0, y1;
     cover_s<S>(Y, g.sy, g.py, g.ky, g.modY, y0, y1);
@@ -333,6 +335,21 @@ __global__ void __launch_bounds__(256) pool_undo_rows_kernel(PoolGeom g, const f
       }
       vstore<VEC>(out + idx, acc);
       if (out16) vemit<VEC>(out16 + idx, acc);
+      if (rowsum) {
+#pragma unroll
+        for (int v = 0; v < VEC; v++) total += acc[v];
+      }
+    }
+  }
+  if (rowsum) {                                 // deterministic block sum -> rowsum[blockIdx.x][plane]
+    __shared__ float sh[8];
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < 8; w++) s += sh[w];
+      rowsum[(size_t)blockIdx.x * gridDim.y + blockIdx.y] = s;
     }
   }
 }
@@ -384,8 +401,10 @@ bool pool_forward(const PoolGeom& g, bool is_max, const float* images, float* ta
 }
 
 template <int VEC, bool MAX>
+// colsum (may be null): on return *colsum_slices > 0 iff the kernel wrote per-(row, plane) sums of its output to `colsum`
 static bool launch_undo(const PoolGeom& g, const float* images, const float* grads, const float* acts, float* targets,
-                        float st, float so, long long total, const float* mask, __nv_bfloat16* t16) {
+                        float st, float so, long long total, const float* mask, __nv_bfloat16* t16, float* colsum,
+                        int* colsum_slices) {
   cudaStream_t s = state().stream;
   const int planes = g.C * g.T;
   const long long per_plane = total / planes;
@@ -397,7 +416,8 @@ static bool launch_undo(const PoolGeom& g, const float* images, const float* gra
     const dim3 rgrid((unsigned)g.H, planes);
     const int sh = pow2_shift(g.N / VEC);
     const int S = (g.sx == g.sy && g.sx <= 2) ? g.sx : 0;
-#define CNB_POOL_UNDO(QQ, SS) pool_undo_rows_kernel<VEC, MAX, QQ, SS><<<rgrid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, mask, sh, t16)
+    if (colsum && colsum_slices) *colsum_slices = g.H;
+#define CNB_POOL_UNDO(QQ, SS) pool_undo_rows_kernel<VEC, MAX, QQ, SS><<<rgrid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, mask, sh, t16, colsum)
     if (q <= 1) { if (S == 1) CNB_POOL_UNDO(1, 1); else if (S == 2) CNB_POOL_UNDO(1, 2); else CNB_POOL_UNDO(1, 0); }
     else { if (S == 1) CNB_POOL_UNDO(2, 1); else if (S == 2) CNB_POOL_UNDO(2, 2); else CNB_POOL_UNDO(2, 0); }
 #undef CNB_POOL_UNDO
@@ -410,17 +430,17 @@ static bool launch_undo(const PoolGeom& g, const float* images, const float* gra
 }
 
 static bool undo(const PoolGeom& g, bool is_max, const float* images, const float* grads, const float* acts,
-                 float* targets, float st, float so, const float* mask, __nv_bfloat16* t16) {
+                 float* targets, float st, float so, const float* mask, __nv_bfloat16* t16, float* colsum, int* colsum_slices) {
   const bool v4 = (g.N % 4 == 0) && aligned16(grads) && aligned16(targets) && (!mask || aligned16(mask)) &&
                   (!is_max || (aligned16(images) && aligned16(acts)));
   const long long ins = (long long)g.W * g.H * g.C * g.T;
   bool emitted;
   if (v4) {
-    if (is_max) emitted = launch_undo<4, true>(g, images, grads, acts, targets, st, so, ins * (g.N / 4), mask, t16);
-    else emitted = launch_undo<4, false>(g, images, grads, acts, targets, st, so, ins * (g.N / 4), mask, t16);
+    if (is_max) emitted = launch_undo<4, true>(g, images, grads, acts, targets, st, so, ins * (g.N / 4), mask, t16, colsum, colsum_slices);
+    else emitted = launch_undo<4, false>(g, images, grads, acts, targets, st, so, ins * (g.N / 4), mask, t16, colsum, colsum_slices);
   } else {
-    if (is_max) emitted = launch_undo<1, true>(g, images, grads, acts, targets, st, so, ins * g.N, mask, t16);
-    else emitted = launch_undo<1, false>(g, images, grads, acts, targets, st, so, ins * g.N, mask, t16);
+    if (is_max) emitted = launch_undo<1, true>(g, images, grads, acts, targets, st, so, ins * g.N, mask, t16, colsum, colsum_slices);
+    else emitted = launch_undo<1, false>(g, images, grads, acts, targets, st, so, ins * g.N, mask, t16, colsum, colsum_slices);
   }
   count_launch();
   CNB_LAUNCH_CHECK("pool_undo");
@@ -428,13 +448,14 @@ static bool undo(const PoolGeom& g, bool is_max, const float* images, const floa
 }
 
 bool max_pool_undo(const PoolGeom& g, const float* images, const float* maxGrads, const float* maxActs,
-                   float* targets, float st, float so, const float* relu_mask, __nv_bfloat16* targets_bf16) {
-  return undo(g, true, images, maxGrads, maxActs, targets, st, so, relu_mask, targets_bf16);
+                   float* targets, float st, float so, const float* relu_mask, __nv_bfloat16* targets_bf16,
+                   float* colsum, int* colsum_slices) {
+  return undo(g, true, images, maxGrads, maxActs, targets, st, so, relu_mask, targets_bf16, colsum, colsum_slices);
 }
 
 bool avg_pool_undo(const PoolGeom& g, const float* avgGrads, float* targets, float st, float so, const float* relu_mask,
-                   __nv_bfloat16* targets_bf16) {
-  return undo(g, false, nullptr, avgGrads, nullptr, targets, st, so, relu_mask, targets_bf16);
+                   __nv_bfloat16* targets_bf16, float* colsum, int* colsum_slices) {
+  return undo(g, false, nullptr, avgGrads, nullptr, targets, st, so, relu_mask, targets_bf16, colsum, colsum_slices);
 }
 
 }  // namespace cnb

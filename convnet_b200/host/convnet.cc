@@ -318,6 +318,12 @@ void ConvNet::Bprop() {                                      // convnet.cc:390-4
     if (!in->IsInput()) {
       const bool want_in = bf16 && i >= 2 && edges_[i - 2]->WantsBf16Deriv();
       e->SetEmitDown(want_in && !in->HasDropout() && !in->HasSeparateDerivPass());
+      // the kernel that writes in's derivative LAST can also sum its channels: that is the bias gradient of the edge below
+      static const bool no_bg = getenv("CONVNET_B200_NO_FUSED_BIAS_GRAD") && getenv("CONVNET_B200_NO_FUSED_BIAS_GRAD")[0] == '1';
+      if (!no_bg && i >= 2 && e->CanProduceBiasGrad() && !in->HasDropout() && !in->HasSeparateDerivPass()) {
+        Edge::BiasGradTarget t;
+        if (edges_[i - 2]->OfferFusedBiasGrad(&t)) e->SetBiasGradRequest(t);
+      }
       e->ComputeDown(out->GetDeriv(), in->GetState(), out->GetState(), in->GetDeriv(), /*overwrite=*/true);
     }
     // the optimizer step of a bucket follows its all-reduce on the side stream once its edges are done with the weights

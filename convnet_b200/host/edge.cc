@@ -96,6 +96,14 @@ void EdgeWithWeight::AppendSgdTensors(std::vector<CnbSgdTensor>& out) {   // src
   }
   num_grads_received_ = 0;
 }
+bool EdgeWithWeight::OfferFusedBiasGrad(BiasGradTarget* t) {
+  if (!BiasIsPerChannel2D()) return false;
+  t->grad_bias = grad_bias_.GetDevData();
+  t->st = GetNumGradsReceived() > 0 ? 1.f : 0.f;
+  t->so = scale_gradients_ / batch_size_;
+  bias_grad_fused_ = true;
+  return true;
+}
 void EdgeWithWeight::UpdateWeights() {                       // src/edge_with_weight.cc:96-107: this edge alone
   std::vector<CnbSgdTensor> t;
   AppendSgdTensors(t);
@@ -206,6 +214,7 @@ void ConvEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, 
   StageForBprop(deriv_output);
   if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());      // ReLU' of the source layer
   if (emit_down_) convnet_b200_emit_bf16_next();
+  ApplyBiasGradRequest();
   if (image_size_t_ == 1) Matrix::ConvDown(deriv_output, weights_, deriv_input, conv_desc_, scale_targets);
   else Matrix::Conv3DDown(deriv_output, weights_, deriv_input, conv_desc_, scale_targets);
   NoteDown();
@@ -223,7 +232,9 @@ void ConvEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {   // :183-245
     Matrix::Conv3DOutp(input, deriv_output, grad_weights_, conv_desc_, scale_targets, scale);
   }
   NoteOuter();
-  if (!has_no_bias_) {
+  const bool bias_done = bias_grad_fused_;            // the edge above summed the channels while it wrote the derivative
+  bias_grad_fused_ = false;
+  if (!has_no_bias_ && !bias_done) {
     if (shared_bias_ && image_size_t_ == 1) {
       // the reference sums in two steps through a temp (:212-218); one deterministic pass here
       deriv_output.Reshape(-1, conv_desc_.num_output_channels);
@@ -303,6 +314,7 @@ void FCEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Ma
   StageForBprop(deriv_output);
   if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
   if (emit_down_) convnet_b200_emit_bf16_next();
+  ApplyBiasGradRequest();
   Matrix::ConvDown(deriv_output, weights_, deriv_input, desc_, overwrite ? 0 : 1);
   NoteDown();
   deriv_input.GetShape4D() = si; deriv_output.GetShape4D() = so;
@@ -315,7 +327,9 @@ void FCEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {                
   StageForBprop(deriv_output);
   Matrix::ConvOutp(input, deriv_output, grad_weights_, desc_, 0, 0, scale_targets, scale_gradients_ / batch_size);
   NoteOuter();
-  if (!has_no_bias_) deriv_output.SumRows(grad_bias_, scale_targets, scale_gradients_ / batch_size);
+  const bool bias_done = bias_grad_fused_;
+  bias_grad_fused_ = false;
+  if (!has_no_bias_ && !bias_done) deriv_output.SumRows(grad_bias_, scale_targets, scale_gradients_ / batch_size);
   input.GetShape4D() = si; deriv_output.GetShape4D() = so;
   IncrementNumGradsReceived();
 }
@@ -362,6 +376,7 @@ void ConvOneToOneEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& 
   StageForBprop(deriv_output);
   if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
   if (emit_down_) convnet_b200_emit_bf16_next();
+  ApplyBiasGradRequest();
   Matrix::ConvDown(deriv_output, weights_, deriv_input, desc_, overwrite ? 0 : 1);
   NoteDown();
 }
@@ -371,7 +386,9 @@ void ConvOneToOneEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {      
   StageForBprop(deriv_output);
   Matrix::ConvOutp(input, deriv_output, grad_weights_, desc_, 0, 0, scale_targets, scale_gradients_ / batch_size);
   NoteOuter();
-  if (!has_no_bias_) {
+  const bool bias_done = bias_grad_fused_;
+  bias_grad_fused_ = false;
+  if (!has_no_bias_ && !bias_done) {
     deriv_output.Reshape(-1, num_output_channels_);
     deriv_output.SumRows(grad_bias_, scale_targets, scale_gradients_ / batch_size);
     deriv_output.Reshape(batch_size, -1);
@@ -405,6 +422,7 @@ void MaxPoolEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool 
 void MaxPoolEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) {
   if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
   if (emit_down_) convnet_b200_emit_bf16_next();
+  ApplyBiasGradRequest();
   Matrix::ConvMaxPoolUndo(input, deriv_output, output, deriv_input, conv_desc_, overwrite ? 0 : 1);
 }
 void AvgPoolEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) {   // avgpool_edge.cc:50-58
@@ -415,6 +433,7 @@ void AvgPoolEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool 
 void AvgPoolEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) {
   if (fuse_mask_) convnet_b200_fuse_next(nullptr, 0, input.GetDevData());
   if (emit_down_) convnet_b200_emit_bf16_next();
+  ApplyBiasGradRequest();
   Matrix::ConvAvgPoolUndo(deriv_output, deriv_input, conv_desc_, overwrite ? 0 : 1);
 }
 

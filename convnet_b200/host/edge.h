@@ -95,6 +95,13 @@ class Edge {
   // emit_down: ComputeDown is the last writer of the source layer's derivative and the edge below multiplies in bf16.
   void SetEmitUp(bool v) { emit_up_ = v; }
   void SetEmitDown(bool v) { emit_down_ = v; }
+  // Fused bias gradient: the edge ABOVE writes this edge's output derivative last, and its kernel can sum the channels
+  // while it stores them (convnet_b200_fuse_next_bias_grad).  ConvNet asks the lower edge for its target (which makes that
+  // edge skip its own SumRows in ComputeOuter) and hands it to the upper edge's ComputeDown.
+  struct BiasGradTarget { float* grad_bias = nullptr; float st = 0.f, so = 1.f; };
+  virtual bool OfferFusedBiasGrad(BiasGradTarget*) { return false; }
+  void SetBiasGradRequest(const BiasGradTarget& t) { bg_request_ = t; }
+  virtual bool CanProduceBiasGrad() const { return false; }   // ComputeDown kernels that take the request
   virtual bool WantsBf16Input() const { return false; }      // this edge reads its input (fprop / wgrad) as bf16
   virtual bool WantsBf16Deriv() const { return false; }      // this edge reads its output derivative (wgrad / dgrad) as bf16
 
@@ -108,6 +115,11 @@ class Edge {
   int batch_size_;
   bool fuse_relu_ = false, fuse_mask_ = false;
   bool emit_up_ = false, emit_down_ = false;
+  BiasGradTarget bg_request_;
+  void ApplyBiasGradRequest() {            // call right before the ComputeDown kernel
+    if (bg_request_.grad_bias) convnet_b200_fuse_next_bias_grad(bg_request_.grad_bias, bg_request_.st, bg_request_.so);
+    bg_request_ = BiasGradTarget();
+  }
 };
 
 class EdgeWithWeight : public Edge {
@@ -133,6 +145,9 @@ class EdgeWithWeight : public Edge {
   bool WantsBf16Input() const override { return bf_up_ == 1 || bf_outer_ == 1; }
   bool WantsBf16Deriv() const override { return bf_outer_ == 1 || bf_down_ == 1; }
   void AppendSgdTensors(std::vector<CnbSgdTensor>& out);                 // weights (+ bias) of this edge for one multi-tensor update
+  bool OfferFusedBiasGrad(BiasGradTarget* t) override;
+  virtual bool BiasIsPerChannel2D() const { return !has_no_bias_; }       // one bias per output channel, 2-D layer
+  bool CanProduceBiasGrad() const override { return true; }
 
  protected:
   void StageForUp(Matrix& input);
@@ -145,6 +160,7 @@ class EdgeWithWeight : public Edge {
   float scale_gradients_;
   int num_grads_received_;
   int bf_up_ = -1, bf_down_ = -1, bf_outer_ = -1;        // -1 unknown, 0 tf32 / fp32 path, 1 bf16 path
+  bool bias_grad_fused_ = false;                         // this step's bias gradient comes from the edge above (ComputeOuter skips SumRows)
 };
 
 class ConvEdge : public EdgeWithWeight {
@@ -162,6 +178,8 @@ class ConvEdge : public EdgeWithWeight {
   ConvDesc GetConvDesc() const { return conv_desc_; }
   bool CanFuseReLU() const override { return !has_no_bias_ && shared_bias_ && image_size_t_ == 1; }
   bool CanFuseMask() const override { return image_size_t_ == 1; }
+  bool BiasIsPerChannel2D() const override { return !has_no_bias_ && shared_bias_ && image_size_t_ == 1; }
+  bool CanProduceBiasGrad() const override { return image_size_t_ == 1; }
 
  private:
   ConvDesc conv_desc_;
@@ -216,6 +234,7 @@ class MaxPoolEdge : public Edge {
   void ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) override;
   void ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) override;
   bool CanFuseMask() const override { return true; }
+  bool CanProduceBiasGrad() const override { return image_size_t_ == 1; }
 
  protected:
   ConvDesc conv_desc_;

@@ -42,6 +42,13 @@ int convnet_b200_last_conv_path(void);
 unsigned long long convnet_b200_launch_count(void);
 void convnet_b200_reset_launch_count(void);
 
+/* One-shot: the NEXT pool-undo (MaxPoolUndo*, AvgPoolUndo*) or convDown* call also produces the shared-bias gradient of
+ * the edge BELOW — the one whose output derivative is the tensor this call writes (src/conv_edge.cc:210-222 runs
+ * SumRows over that tensor later):  grad_bias[c] = scaleTargets*grad_bias[c] + scaleOutput * sum_{n,pixels} target[n,pixel,c].
+ * The sums come from the values the kernel is storing anyway (deterministic per-row partial sums + a tiny second
+ * kernel), so the separate pass over the derivative disappears; calls that cannot do it run that pass themselves. */
+void convnet_b200_fuse_next_bias_grad(float* grad_bias, float scaleTargets, float scaleOutput);
+
 /* The conv kernels are persistent: one CTA (or CTA pair) per SM, each owning most of the SM's shared memory.  A kernel
  * of another library that must run CONCURRENTLY (an NCCL collective on a side stream) cannot co-reside with them and
  * would otherwise wait for — or push out — a whole wave.  convnet_b200_reserve_sms(n) makes the persistent grids leave
