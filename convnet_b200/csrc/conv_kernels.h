@@ -37,6 +37,19 @@ void bf16_note_write(const float* ptr, long long n);                   // [ptr, 
 __nv_bfloat16* bf16_emit_slot(const float* ptr, long long n);          // buffer a producing kernel fills itself (marked valid)
 __nv_bfloat16* bf16_refresh_slot(const float* ptr, long long n);       // the existing buffer of exactly this tensor, or nullptr
 void bf16_release();                                                   // drops the buffers too
+// dgrad in fprop form (stage.cu): stride phases and the per-phase filter banks [c][tap''][o]
+constexpr int kMaxDgradPhases = 16;
+struct DgradPhase {
+  int a, b;            // input pixel phase: x = sx*i + a, y = sy*j + b
+  int rx, ry;          // tap residues: tx = rx + sx*u
+  int ku, kv;          // taps of this phase
+  int px, py;          // (negative) window start offsets of the stride-1 correlation over the derivative
+  int Wp, Hp;          // pixels of this phase
+  long long offset;    // element offset of the phase's bank
+};
+struct DgradBanks { int count; DgradPhase phase[kMaxDgradPhases]; };
+int dgrad_phases(const ConvGeom& g, DgradBanks* b);                    // number of phases, or -1 if there are too many
+const __nv_bfloat16* dgrad_weights(const float* filters, const ConvGeom& g, const DgradBanks& b);   // built on first use, cached
 // writer protocol: begin_write drops stale copies and returns the buffer the kernel must fill when it can emit; end_write
 // falls back to a conversion pass when emission was wanted but the kernel could not do it
 __nv_bfloat16* begin_write(float* target, long long n, bool want_emit, bool kernel_can_emit);

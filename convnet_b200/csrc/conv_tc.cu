@@ -81,6 +81,11 @@ struct TcParams {
   int ksteps;                       // UMMA K-steps per stage: 4 (64 K elements) or 8 (128)
   uint32_t a_stage_bytes;           // 128 rows x (16 * ksteps) bf16
   int b_chunks;                     // fprop: 64-column chunks of B this CTA stages per k-block
+  // fast fprop: where output position (i, j) of the modX x modY grid lands in the target tensor: pixel
+  // (i*o_sx + o_x0, j*o_sy + o_y0) of an o_W-wide plane of out_plane pixels.  Plain fprop: identity.  dgrad run as a
+  // stride-1 correlation per stride phase (tc_conv_down_as_fprop) writes every o_sx-th pixel.
+  int o_sx, o_sy, o_x0, o_y0, o_W;
+  long long out_plane;
 };
 
 struct __align__(8) SmemCtl {
@@ -869,14 +874,18 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         const int n_tile = t % p.n_tiles, mg = t / p.n_tiles;
         const int m_tile = PAIR ? 2 * mg + rank : mg;
         const int qc = m_tile * 2 + (quarter >> 1);                  // this warp's 32 rows are half of one 64-image chunk
-        const int per_frame = (OP == kFprop) ? p.modules : p.W * p.H;
-        col_stride = (long long)p.N * per_frame;
+        col_stride = (OP == kFprop) ? (long long)p.N * p.out_plane : (long long)p.N * p.W * p.H;
         col0 = n_tile * p.BN;
         ncols = min(p.BN, (OP == kFprop ? p.Cout : p.Cin) - col0);
         if (qc < p.total_chunks) {
           const int ib = qc % p.nbc, pos = qc / p.nbc;
           const int n = ib * 64 + (quarter & 1) * 32 + lane;
-          row_ptr = p.out + n + (long long)p.N * pos + col_stride * col0;
+          long long opos = pos;
+          if (OP == kFprop) {
+            const int i = pos % p.modX, j = pos / p.modX;
+            opos = (long long)(j * p.o_sy + p.o_y0) * p.o_W + i * p.o_sx + p.o_x0;
+          }
+          row_ptr = p.out + n + (long long)p.N * opos + col_stride * col0;
         }
       } else {
         int tt = t;
@@ -906,13 +915,28 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 #pragma unroll
           for (int j = 0; j < 32; j++) bv[j] = bp ? __ldg(bp + j) : 0.f;
           const bool relu = p.relu != 0;
+          if (p.mask == nullptr) {
 #pragma unroll
-          for (int j = 0; j < 32; j++) {
-            float r = fmaf(p.so, v[j], bv[j]);
-            r = relu ? fmaxf(r, 0.f) : r;
-            *dst = r;
-            if (dst16) { *dst16 = __float2bfloat16_rn(r); dst16 += col_stride; }
-            dst += col_stride;
+            for (int j = 0; j < 32; j++) {
+              float r = fmaf(p.so, v[j], bv[j]);
+              r = relu ? fmaxf(r, 0.f) : r;
+              *dst = r;
+              if (dst16) { *dst16 = __float2bfloat16_rn(r); dst16 += col_stride; }
+              dst += col_stride;
+            }
+          } else {                                                   // dgrad in fprop form: ReLU' of the layer receiving the derivative
+            float mk[32];
+            const float* mp = p.mask + (dst - p.out);
+#pragma unroll
+            for (int j = 0; j < 32; j++) { mk[j] = __ldg(mp); mp += col_stride; }
+#pragma unroll
+            for (int j = 0; j < 32; j++) {
+              float r = fmaf(p.so, v[j], bv[j]);
+              r = mk[j] > 0.f ? r : 0.f;
+              *dst = r;
+              if (dst16) { *dst16 = __float2bfloat16_rn(r); dst16 += col_stride; }
+              dst += col_stride;
+            }
           }
         } else if (OP == kDgrad) {
           float mk[32];
@@ -1157,6 +1181,8 @@ void fill_common(TcParams& p, const ConvGeom& g, const Elem& e) {
   static const int dbg = getenv("CONVNET_B200_TC_DEBUG") ? atoi(getenv("CONVNET_B200_TC_DEBUG")) : 0;
   p.dbg = dbg;
   p.bias = nullptr; p.relu = 0; p.mask = nullptr; p.out16 = nullptr;
+  p.o_sx = p.o_sy = 1; p.o_x0 = p.o_y0 = 0; p.o_W = g.modX; p.out_plane = g.modules;
+  p.ksteps = 4; p.a_stage_bytes = kAStageBytes; p.b_chunks = 0;
   p.out_frame_step = g.out_frame_step;
   p.total_chunks = 0;
 }
@@ -1389,6 +1415,82 @@ bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, fl
   return tc_conv_up_impl(g, images, filters, targets, st, so, fuse, false);
 }
 
+
+// ---- dgrad in fprop form ---------------------------------------------------------------------------------------------
+// dInput[n, x, y, c] = sum_{o, taps} der[n, module, o] * w[o, tap, c] is, for the input pixels of one stride phase, a STRIDE-1
+// correlation of the derivative with the phase's flipped taps (stage.cu: dgrad_weights).  In that form it is exactly the fprop
+// GEMM — A = derivative (MN-major, one request per tile), B = filter bank [c][tap''][o] (MN-major) — and runs on the fprop
+// flavour of tc_fast_kernel: CTA pairs, both operands MN-major, no dead taps.  The gather kernel above, with its K-major B
+// of 256 rows per k-block per CTA, measured L2-feed-bound at 0.2-0.4 of the fprop rate on the same problem
+// (profiles/r2_layer_probe_fast_v1.log).  One launch per stride phase; the epilogue writes every sx-th / sy-th pixel.
+static bool tc_conv_down_as_fprop(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float so,
+                                  const Fuse& fuse) {
+  static const bool off = getenv("CONVNET_B200_NO_DGRAD_AS_FPROP") && getenv("CONVNET_B200_NO_DGRAD_AS_FPROP")[0] == '1';
+  if (off || !fast_enabled() || !g.conv || g.frames != 1) return false;
+  if (g.cin0 != 0 || g.Cin != g.CinT || g.cout0 != 0 || g.Cout != g.CoutT) return false;
+  if (g.N % 128 != 0 || g.Cin % 32 != 0 || g.Cout % 8 != 0 || !aligned16(derivs) || !aligned16(filters)) return false;
+  if ((long long)g.N * g.W * g.H < 1024) return false;                      // FC-shaped: weight-streaming bound, stays tf32
+  DgradBanks banks;
+  if (dgrad_phases(g, &banks) <= 0) return false;
+  for (int i = 0; i < banks.count; i++) if (banks.phase[i].ku == 0 || banks.phase[i].kv == 0) return false;
+  const Elem e = elem_for(true);
+  // the derivative as bf16 (staged by the producer, or converted here)
+  const __nv_bfloat16* sd = bf16_staged(derivs, g.out_total);
+  if (!sd) {
+    __nv_bfloat16* tmp = (__nv_bfloat16*)workspace(align_up((size_t)g.out_total * 2));
+    to_bf16(derivs, tmp, g.out_total);
+    sd = tmp;
+  }
+  const __nv_bfloat16* bank = dgrad_weights(filters, g, banks);
+  bool emitted_all = fuse.out16 != nullptr;
+  for (int i = 0; i < banks.count; i++) {
+    const DgradPhase& P = banks.phase[i];
+    TcParams p; fill_common(p, g, e);
+    // the GEMM of this phase: rows = (image, phase pixel), K = (tap'', o), columns = input channels
+    p.modX = P.Wp; p.modY = P.Hp; p.modules = P.Wp * P.Hp;
+    p.W = g.modX; p.H = g.modY;                        // the tensor A is read from (the derivative grid)
+    p.kx = P.ku; p.ky = P.kv; p.taps = P.ku * P.kv; p.sx = p.sy = 1; p.px = P.px; p.py = P.py;
+    p.Cin = g.Cout; p.Cout = g.Cin;
+    p.BN = pick_bn(g.Cin, 32);
+    p.total_chunks = p.nbc * p.modules;
+    p.m_tiles = ceil_div(p.total_chunks, p.cpt);
+    p.n_tiles = ceil_div(g.Cin, p.BN);
+    p.num_tiles = p.m_tiles * p.n_tiles;
+    p.out = targets; p.st = 0.f; p.so = so;
+    p.mask = fuse.relu_mask; p.out16 = fuse.out16;
+    p.o_sx = g.sx; p.o_sy = g.sy; p.o_x0 = P.a; p.o_y0 = P.b; p.o_W = g.W; p.out_plane = (long long)g.W * g.H;
+    p.idesc = ptx::make_idesc(1, true, true, BM, p.BN);
+    apply_pair(p, kFprop, 16, 1);
+    const int bn_local = p.cta2 ? p.BN / 2 : p.BN;
+    p.b_chunks = ceil_div(bn_local, 64);
+    p.b_merged = (g.Cin % 64 == 0 && bn_local % 64 == 0 && p.BN % 64 == 0) ? 1 : 0;
+    if (!fast_pick_stages(p, p.b_chunks * 64)) return false;
+    Elem e2 = e; e2.bk = p.ksteps * 16;
+    p.kc_blocks = ceil_div(g.Cout, e2.bk);
+    ConvGeom gd = g;                                   // merged_image_map only reads N from the geometry
+    CUtensorMap fa, fb;
+    if (!merged_image_map(&fa, sd, e2, gd, g.modX, g.modY, g.Cout, false)) return false;
+    const __nv_bfloat16* wb = bank + P.offset;
+    bool ok;
+    if (p.b_merged) {
+      const long long dims[4] = {64, g.Cout, g.Cin / 64, p.taps};
+      const long long str[3] = {(long long)g.Cin * p.taps, 64, g.Cin};
+      const int box[4] = {64, e2.bk, p.b_chunks, 1};
+      ok = make_map(&fb, wb, e2, 4, dims, str, box, true);
+    } else {
+      const long long dims[3] = {g.Cin, p.taps, g.Cout};
+      const long long str[2] = {g.Cin, (long long)g.Cin * p.taps};
+      const int box[3] = {64, 1, e2.bk};
+      ok = make_map(&fb, wb, e2, 3, dims, str, box, true);
+    }
+    if (!ok) { CNB_REQUIRE(i == 0, "dgrad-as-fprop: tensor map failed after the first phase"); return false; }
+    launch_fast<kFprop>(fa, fb, p);
+  }
+  if (emitted_all && fuse.emitted) *fuse.emitted = true;
+  state().last_conv_path = kPathTcBf16;
+  return true;
+}
+
 // ---- dgrad ---------------------------------------------------------------------------------------
 static bool tc_conv_down_impl(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float st, float so,
                               const Fuse& fuse, bool bf) {
@@ -1455,17 +1557,7 @@ static bool tc_conv_down_impl(const ConvGeom& g, const float* derivs, const floa
   } else if (whole) {
     p.st = st; p.out = out; p.mask = fuse.relu_mask ? fuse.relu_mask + (long long)g.cin0 * g.H * g.W * g.N : nullptr;
     p.out16 = fuse.out16;                              // `whole`: every element gets its final value here
-    bool done = false;
-    if (bf && fast_enabled() && p.a_merged && !p.cta2 && st == 0.f && g.Cin % 32 == 0 && p.BN % 32 == 0 && g.Cout % 8 == 0) {
-      TcParams f = p;
-      if (fast_pick_stages(f, bn_local)) {
-        Elem e2 = e; e2.bk = f.ksteps * 16;
-        f.kc_blocks = ceil_div(g.Cout, e2.bk);
-        CUtensorMap fa;
-        if (merged_image_map(&fa, der, e2, g, g.modX, g.modY, g.Cout, false)) { launch_fast<kDgrad>(fa, mb, f); done = true; }
-      }
-    }
-    if (!done) launch<kDgrad>(ma, mb, p);
+    launch<kDgrad>(ma, mb, p);
     if (fuse.out16 && fuse.emitted) *fuse.emitted = true;
   } else {
     // the reference scales the WHOLE target first (gemm.cu:760, conv3d_gemm.cu:98); frame windows overlap,
@@ -1483,6 +1575,7 @@ static bool tc_conv_down_impl(const ConvGeom& g, const float* derivs, const floa
 bool tc_conv_down(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float st, float so,
                   const Fuse& fuse) {
   if (!tc_enabled() || !g.conv) return false;
+  if (want_bf16() && st == 0.f && tc_conv_down_as_fprop(g, derivs, filters, targets, so, fuse)) return true;
   if (want_bf16() && tc_conv_down_impl(g, derivs, filters, targets, st, so, fuse, true)) return true;
   return tc_conv_down_impl(g, derivs, filters, targets, st, so, fuse, false);
 }

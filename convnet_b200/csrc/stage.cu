@@ -21,6 +21,8 @@ namespace {
 
 struct Staged {
   const float* src; long long n; __nv_bfloat16* buf; size_t cap; bool valid; unsigned long long tick; int dev;
+  int kind;                         // 0: plain bf16 copy; 1: dgrad weight banks (dgrad_weights), `sig` = geometry they were built for
+  unsigned long long sig;
 };
 std::vector<Staged>& table() { static std::vector<Staged> t; return t; }
 unsigned long long g_tick = 0;
@@ -76,22 +78,22 @@ void verify(const Staged& e, long long n) {
   }
 }
 
-Staged* find_slot(const float* ptr, int dev) {
-  for (Staged& e : table()) if (e.src == ptr && e.dev == dev) return &e;
+Staged* find_slot(const float* ptr, int dev, int kind = 0) {
+  for (Staged& e : table()) if (e.src == ptr && e.dev == dev && e.kind == kind) return &e;
   return nullptr;
 }
 
 // slot for [ptr, ptr+n) with a buffer of at least n bf16; contents undefined, valid == false
-Staged* acquire_slot(const float* ptr, long long n) {
+Staged* acquire_slot(const float* ptr, long long n, int kind = 0) {
   std::vector<Staged>& t = table();
   const int dev = current_device();
-  Staged* slot = find_slot(ptr, dev);
+  Staged* slot = find_slot(ptr, dev, kind);
   if (!slot) {
     if (t.size() >= kMaxStaged) {                                       // recycle the least recently used entry
       slot = &t[0];
       for (Staged& e : t) if (e.tick < slot->tick) slot = &e;
     } else {
-      t.push_back(Staged{ptr, 0, nullptr, 0, false, 0, dev});
+      t.push_back(Staged{ptr, 0, nullptr, 0, false, 0, dev, kind, 0});
       slot = &t.back();
     }
   }
@@ -107,9 +109,76 @@ Staged* acquire_slot(const float* ptr, long long n) {
     CNB_CUDA_CHECK(cudaMalloc((void**)&slot->buf, bytes));
     slot->cap = bytes;
   }
-  slot->src = ptr; slot->n = n; slot->dev = dev; slot->valid = false; slot->tick = ++g_tick;
+  slot->src = ptr; slot->n = n; slot->dev = dev; slot->valid = false; slot->tick = ++g_tick; slot->kind = kind; slot->sig = 0;
   return slot;
 }
+
+
+// ---- dgrad weight banks ---------------------------------------------------------------------------------------------
+// dgrad is a stride-1 correlation of the output derivative with the flipped filters — one per stride phase (a, b) of the
+// input pixel (x = sx*i + a, y = sy*j + b), each phase seeing only the taps congruent to (a + pad) mod stride.  Run in that
+// form it uses the fprop kernel (CTA pairs, MN-major B), which needs the filters of a phase as [c fastest][tap''][o]:
+//   bank(a,b)[c + Cin*((u' + ku*v') + ku*kv*o)] = w[o, tx = ra + sx*(ku-1-u'), ty = rb + sy*(kv-1-v'), c]
+// (reference semantics: cudamat_conv_gemm.cu:684-825, convDown = Sgemm + kContract).  The banks are a permutation of the
+// filter tensor (every tap belongs to exactly one phase), built by one small kernel and cached like a bf16 copy.
+__global__ void __launch_bounds__(256) dgrad_bank_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, DgradBanks b,
+                                                         int Cin, int Cout, int kx, int ky, int sx, int sy) {
+  const long long total = (long long)Cin * Cout * kx * ky;
+  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
+    int ph = 0;
+    while (ph + 1 < b.count && idx >= b.phase[ph + 1].offset) ph++;
+    const DgradPhase& P = b.phase[ph];
+    const long long l = idx - P.offset;
+    const int T = P.ku * P.kv;
+    const int c = (int)(l % Cin), t = (int)((l / Cin) % T), o = (int)(l / ((long long)Cin * T));
+    const int u = t % P.ku, v = t / P.ku;
+    const int tx = P.rx + sx * (P.ku - 1 - u), ty = P.ry + sy * (P.kv - 1 - v);
+    out[idx] = __float2bfloat16_rn(w[o + (long long)Cout * (tx + kx * (ty + ky * c))]);
+  }
+}
+
+}  // namespace
+
+int dgrad_phases(const ConvGeom& g, DgradBanks* b) {
+  const int pad_x = -g.px, pad_y = -g.py;
+  b->count = 0;
+  long long off = 0;
+  for (int pb = 0; pb < g.sy; pb++)
+    for (int pa = 0; pa < g.sx; pa++) {
+      if (pa >= g.W || pb >= g.H) continue;
+      DgradPhase P;
+      P.a = pa; P.b = pb;
+      P.rx = (pa + pad_x) % g.sx; P.ry = (pb + pad_y) % g.sy;
+      P.ku = P.rx < g.kx ? (g.kx - 1 - P.rx) / g.sx + 1 : 0;
+      P.kv = P.ry < g.ky ? (g.ky - 1 - P.ry) / g.sy + 1 : 0;
+      P.px = (pa + pad_x - P.rx) / g.sx - (P.ku - 1);
+      P.py = (pb + pad_y - P.ry) / g.sy - (P.kv - 1);
+      P.Wp = (g.W - pa + g.sx - 1) / g.sx; P.Hp = (g.H - pb + g.sy - 1) / g.sy;
+      P.offset = off;
+      off += (long long)g.Cin * g.Cout * P.ku * P.kv;
+      if (b->count >= kMaxDgradPhases) return -1;
+      b->phase[b->count++] = P;
+    }
+  return b->count;
+}
+
+const __nv_bfloat16* dgrad_weights(const float* filters, const ConvGeom& g, const DgradBanks& b) {
+  const long long n = (long long)g.Cout * g.K;
+  unsigned long long sig = 1469598103934665603ULL;
+  for (int v : {g.Cin, g.Cout, g.kx, g.ky, g.sx, g.sy, g.px, g.py, g.W, g.H}) sig = (sig ^ (unsigned)v) * 1099511628211ULL;
+  const int dev = current_device();
+  Staged* e = find_slot(filters, dev, 1);
+  if (e && e->valid && e->n == n && e->sig == sig) { e->tick = ++g_tick; return e->buf; }
+  e = acquire_slot(filters, n, 1);
+  const int grid = (int)std::min<long long>(std::max<long long>(ceil_div<long long>(n, 256), 1), 8LL * num_sms());
+  dgrad_bank_kernel<<<grid, 256, 0, state().stream>>>(filters, e->buf, b, g.Cin, g.Cout, g.kx, g.ky, g.sx, g.sy);
+  count_launch();
+  CNB_LAUNCH_CHECK("dgrad_banks");
+  e->valid = true; e->sig = sig;
+  return e->buf;
+}
+
+namespace {
 
 }  // namespace
 
@@ -129,7 +198,7 @@ const __nv_bfloat16* bf16_staged(const float* src, long long n) {          // nu
   if (table().empty()) return nullptr;
   const int dev = current_device();
   for (Staged& e : table())
-    if (e.valid && e.src == src && e.dev == dev && e.n >= n) {
+    if (e.valid && e.kind == 0 && e.src == src && e.dev == dev && e.n >= n) {
       e.tick = ++g_tick;
       if (verify_enabled()) verify(e, n);
       return e.buf;
@@ -184,7 +253,7 @@ __nv_bfloat16* bf16_emit_slot(const float* ptr, long long n) {
 
 __nv_bfloat16* bf16_refresh_slot(const float* ptr, long long n) {
   if (!want_bf16() || table().empty()) return nullptr;
-  Staged* e = find_slot(ptr, current_device());
+  Staged* e = find_slot(ptr, current_device(), 0);
   if (!e || e->n != n || !e->buf) return nullptr;
   e->valid = true; e->tick = ++g_tick;
   return e->buf;
