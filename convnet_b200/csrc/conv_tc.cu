@@ -646,7 +646,9 @@ struct FastTile {
   int b0;                           // B coordinate fixed for the tile
 };
 
-template <int OP, bool PAIR>
+// XM: the tf32 "x mode" for tiny channel counts (the RGB first layer), see TcParams::x_mode — fprop: one k-block per
+// channel = 8 x-taps x 8 filter rows (64 K rows, eight UMMA steps of 8); wgrad: the N tile is (channels x ky rows x 8 taps).
+template <int OP, bool PAIR, bool XM>
 __global__ void __launch_bounds__(kThreads, 1)
 tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -696,7 +698,23 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1u; a_addr = a_base; b_addr = b_base; bar_off = 0; }
 
     for (int t = t_first; t < p.num_tiles; t += t_step, tcount++) {
-      if (OP == kFprop) {
+      if (OP == kFprop && XM) {
+        const int n_tile = t % p.n_tiles, m_tile = t / p.n_tiles;
+        const int q = m_tile * 4;                                     // first 32-image chunk of the tile
+        const bool ok = q < p.total_chunks;
+        const int ib = q % p.nb, pos = q / p.nb;
+        const int n_hi = ok ? ib : p.nb;
+        const int cX = (pos % p.modX) * p.sx + p.px, cY = (pos / p.modX) * p.sy + p.py;
+        if (elected) ctl->tile_nkb[tcount & 15] = p.Cin;
+        for (int c = 0; c < p.Cin; c++) {
+          CNB_STAGE_BEGIN();
+          if (elected) {
+            ptx::tma5_a<PAIR>(&mapA, fullb, a_addr, 0, cX, cY, n_hi, c);                          // dims (n_lo, x, y, n_hi, c): 8 x 8 taps
+            ptx::tma5_a<PAIR>(&mapB, fullb, b_addr, 0, 0, 0, n_tile * (p.BN >> 5), c);            // dims (o_lo, tx, ty, o_hi, c)
+          }
+          CNB_STAGE_END();
+        }
+      } else if (OP == kFprop) {
         const int n_tile = t % p.n_tiles, mg = t / p.n_tiles;
         const int m_tile = PAIR ? 2 * mg + rank : mg;
         const int q = m_tile * 2;                                     // first 64-image chunk of the tile
@@ -765,6 +783,24 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
               CNB_STAGE_END();
             }
           }
+      } else if (XM) {
+        // x-mode wgrad tile (o_tile, c_tile, split): all modules of the split's rows; B = x_ct channels x ky rows x 8 taps
+        int tt = t;
+        const int split = tt % p.splits; tt /= p.splits;
+        const int c_tile = tt % p.n_tiles; const int o_tile = tt / p.n_tiles;
+        const int r0 = split * p.units_per_split, r1 = min(r0 + p.units_per_split, p.modY);
+        const int cps = p.ksteps >> 2, nsteps = p.nb / cps;              // 32-image chunks per stage
+        if (elected) ctl->tile_nkb[tcount & 15] = max(r1 - r0, 0) * p.modX * nsteps;
+        for (int my = r0; my < r1; my++)
+          for (int mx = 0; mx < p.modX; mx++)
+            for (int ib = 0; ib < nsteps; ib++) {
+              CNB_STAGE_BEGIN();
+              if (elected) {
+                ptx::tma5_a<PAIR>(&mapA, fullb, a_addr, 0, mx, my, o_tile * BM, cps * ib);       // dims (n_lo, mx, my, o, n_hi)
+                ptx::tma5_a<PAIR>(&mapB, fullb, b_addr, 0, mx * p.sx + p.px, my * p.sy + p.py, c_tile * p.x_ct, cps * ib);   // (n_lo, x, y, c, n_hi)
+              }
+              CNB_STAGE_END();
+            }
       } else {
         // wgrad tile (tap, o_tile, c_tile, split): sum over the module rows of this split whose tap lands inside the image
         int tt = t;
@@ -821,12 +857,20 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     // operand layouts exactly as in tc_conv_kernel; K-steps inside a stage: MN-major operands advance by 16 rows of 128 B,
     // K-major ones by 32 B inside a 64-element panel and by one panel (rows * 128 B) after four steps
     const bool a_mn = (OP != kWgrad), b_mn = (OP == kFprop);
-    const uint32_t mn_lbo = (uint32_t)bk * 128u;
-    const uint32_t b_rows_local = (uint32_t)bn_local;
-    const uint64_t da_base = ptx::make_smem_desc(ptx::smem_u32(smemA), a_mn ? mn_lbo : 16u, 1024u, ptx::kLayoutSw128);
-    const uint64_t db_base = ptx::make_smem_desc(ptx::smem_u32(smemB), b_mn ? mn_lbo : 16u, 1024u, ptx::kLayoutSw128);
-    const uint32_t a_lo = a_mn ? 128u : 2u, a_hi = a_mn ? 512u : (uint32_t)(BM * 128 >> 4);          // descriptor units of 16 B
-    const uint32_t b_lo = b_mn ? 128u : 2u, b_hi = b_mn ? 512u : (b_rows_local * 128u) >> 4;
+    // MN-major tiles are [chunk][K rows][128 B]: bf16 in SWIZZLE_128B (8-row groups, 16 rows per UMMA step), tf32 (XM) in
+    // SWIZZLE_128B_BASE32B (4-row groups, 8 rows per step); LBO = one chunk of K rows
+    const uint32_t mn_rows = XM ? 64u : (uint32_t)bk;
+    const uint32_t mn_lbo = mn_rows * 128u, mn_sbo = XM ? 512u : 1024u;
+    const uint32_t mn_lay = XM ? ptx::kLayoutSw128Base32 : ptx::kLayoutSw128;
+    // K-major B rows per panel: the columns of the tile (x-mode wgrad: the x_ct * ky * 8 tap rows the TMA box delivers)
+    const uint32_t b_rows_local = (OP == kWgrad && XM) ? (uint32_t)(p.x_ct * p.ky * 8) : (uint32_t)bn_local;
+    const uint64_t da_base = ptx::make_smem_desc(ptx::smem_u32(smemA), a_mn ? mn_lbo : 16u, a_mn ? mn_sbo : 1024u, a_mn ? mn_lay : ptx::kLayoutSw128);
+    const uint64_t db_base = ptx::make_smem_desc(ptx::smem_u32(smemB), b_mn ? mn_lbo : 16u, b_mn ? mn_sbo : 1024u, b_mn ? mn_lay : ptx::kLayoutSw128);
+    // K-step offsets in descriptor units of 16 B: MN-major = the rows of one step (bf16: 16 x 128 B, tf32: 8 x 128 B);
+    // K-major = 32 B inside a 128-byte panel row, then one panel (rows x 128 B) after four steps
+    const uint32_t mn_step = XM ? 64u : 128u;
+    const uint32_t a_lo = a_mn ? mn_step : 2u, a_hi = a_mn ? 4u * mn_step : (uint32_t)(BM * 128 >> 4);
+    const uint32_t b_lo = b_mn ? mn_step : 2u, b_hi = b_mn ? 4u * mn_step : (b_rows_local * 128u) >> 4;
     const uint32_t a_stage_u = p.a_stage_bytes >> 4, b_stage_u = b_stage_bytes >> 4;
     const bool elected = ptx::elect_one();
     uint32_t stage = 0, phase = 0, bar_off = 0, a_off = 0, b_off = 0;
@@ -845,12 +889,16 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         if (elected) {
           const uint64_t da0 = da_base + a_off, db0 = db_base + b_off;
 #pragma unroll
-          for (int ks = 0; ks < 4; ks++)
-            ptx::mma_bf16_a<PAIR>(d_tmem, da0 + ks * a_lo, db0 + ks * b_lo, p.idesc, (uint32_t)((kb | ks) != 0));
+          for (int ks = 0; ks < 4; ks++) {
+            if constexpr (XM) ptx::mma_tf32_a<PAIR>(d_tmem, da0 + ks * a_lo, db0 + ks * b_lo, p.idesc, (uint32_t)((kb | ks) != 0));
+            else ptx::mma_bf16_a<PAIR>(d_tmem, da0 + ks * a_lo, db0 + ks * b_lo, p.idesc, (uint32_t)((kb | ks) != 0));
+          }
           if (p.ksteps == 8) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ks++)
-              ptx::mma_bf16_a<PAIR>(d_tmem, da0 + a_hi + ks * a_lo, db0 + b_hi + ks * b_lo, p.idesc, 1u);
+            for (int ks = 0; ks < 4; ks++) {
+              if constexpr (XM) ptx::mma_tf32_a<PAIR>(d_tmem, da0 + a_hi + ks * a_lo, db0 + b_hi + ks * b_lo, p.idesc, 1u);
+              else ptx::mma_bf16_a<PAIR>(d_tmem, da0 + a_hi + ks * a_lo, db0 + b_hi + ks * b_lo, p.idesc, 1u);
+            }
           }
           ptx::mma_commit_a<PAIR>(bar_empty0 + bar_off);                                  // frees the slot (both CTAs in pair mode)
           if (kb == nkb - 1) ptx::mma_commit_a<PAIR>(tfull0 + acc * 8);
@@ -873,13 +921,15 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       if (OP == kFprop || OP == kDgrad) {
         const int n_tile = t % p.n_tiles, mg = t / p.n_tiles;
         const int m_tile = PAIR ? 2 * mg + rank : mg;
-        const int qc = m_tile * 2 + (quarter >> 1);                  // this warp's 32 rows are half of one 64-image chunk
+        // this warp's 32 rows: half of one 64-image chunk (bf16), or one whole 32-image chunk (tf32 x mode)
+        const int qc = XM ? m_tile * 4 + quarter : m_tile * 2 + (quarter >> 1);
         col_stride = (OP == kFprop) ? (long long)p.N * p.out_plane : (long long)p.N * p.W * p.H;
         col0 = n_tile * p.BN;
         ncols = min(p.BN, (OP == kFprop ? p.Cout : p.Cin) - col0);
         if (qc < p.total_chunks) {
-          const int ib = qc % p.nbc, pos = qc / p.nbc;
-          const int n = ib * 64 + (quarter & 1) * 32 + lane;
+          const int cpp = XM ? p.nb : p.nbc;                          // chunks per position
+          const int ib = qc % cpp, pos = qc / cpp;
+          const int n = XM ? ib * 32 + lane : ib * 64 + (quarter & 1) * 32 + lane;
           long long opos = pos;
           if (OP == kFprop) {
             const int i = pos % p.modX, j = pos / p.modX;
@@ -891,13 +941,19 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
         int tt = t;
         const int split = tt % p.splits; tt /= p.splits;
         const int c_tile = tt % p.n_tiles; tt /= p.n_tiles;
-        int o_tile = tt % p.m_groups; tt /= p.m_groups;
+        int o_tile = XM ? tt : tt % p.m_groups;                      // x mode has no tap level: tt is the o tile
+        if (!XM) tt /= p.m_groups;
         if (PAIR) o_tile = 2 * o_tile + rank;
         const int o = o_tile * BM + quarter * 32 + lane;
         col0 = c_tile * p.BN;
         col_stride = (long long)p.Cout * p.taps;
         ncols = min(p.BN, p.Cin - col0);
-        if (o < p.Cout) row_ptr = p.out + (long long)split * p.Cout * p.taps * p.Cin + o + (long long)p.Cout * tt + col_stride * col0;
+        if (XM) {                                                    // tile = (o_tile, c_tile, split); columns are (tap, row, channel)
+          col0 = c_tile * p.x_ct;
+          ncols = p.x_ct * p.ky * 8;
+          if (o < p.Cout) row_ptr = p.out + (long long)split * p.Cout * p.taps * p.Cin + o;
+        } else if (o < p.Cout)
+          row_ptr = p.out + (long long)split * p.Cout * p.taps * p.Cin + o + (long long)p.Cout * tt + col_stride * col0;
       }
       ptx::mbar_wait_a(tfull0 + acc * 8, acc_phase);
       ptx::tc_fence_after();
@@ -949,6 +1005,13 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
             *dst = r;
             if (dst16) { *dst16 = __float2bfloat16_rn(r); dst16 += col_stride; }
             dst += col_stride;
+          }
+        } else if (XM) {
+          // column jg = tap tx + 8 * (row ty + ky * channel): scattered to dW[o, tx + kx*(ty + ky*c)]
+#pragma unroll
+          for (int j = 0; j < 32; j++) {
+            const int jg = j0 + j, tx = jg & 7, rr = jg >> 3, ty = rr % p.ky, c = col0 + rr / p.ky;
+            if (jg < ncols && tx < p.kx && c < p.Cin) row_ptr[(long long)p.Cout * (tx + p.kx * (ty + p.ky * c))] = p.so * v[j];
           }
         } else {
 #pragma unroll
@@ -1124,20 +1187,20 @@ bool fast_pick_stages(TcParams& p, int b_rows_per_kstep4) {
   }
   return false;
 }
-template <int OP>
+template <int OP, bool XM = false>
 void launch_fast(const CUtensorMap& a, const CUtensorMap& b, TcParams& p) {
   p.tmem_cols = tmem_cols_for(p.BN);
   const size_t smem = fast_smem_bytes(p.a_stage_bytes, (size_t)p.b_rows * 128, p.stages);
   static unsigned long long attr_devices = 0;
   const int dev = current_device();
   if (dev >= 64 || !((attr_devices >> dev) & 1ULL)) {
-    CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_fast_kernel<OP, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    if (OP != kDgrad)
-      CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_fast_kernel<OP, OP != kDgrad>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_fast_kernel<OP, false, XM>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if (!XM)
+      CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_fast_kernel<OP, !XM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (dev < 64) attr_devices |= 1ULL << dev;
   }
   if (p.cta2) {
-    if constexpr (OP != kDgrad) {
+    if constexpr (!XM) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(2u * (unsigned)std::min(p.num_tiles, num_sms() / 2));
       cfg.blockDim = dim3(kThreads);
@@ -1147,11 +1210,11 @@ void launch_fast(const CUtensorMap& a, const CUtensorMap& b, TcParams& p) {
       attr[0].id = cudaLaunchAttributeClusterDimension;
       attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
       cfg.attrs = attr; cfg.numAttrs = 1;
-      CNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_fast_kernel<OP, OP != kDgrad>, a, b, p));
+      CNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_fast_kernel<OP, !XM, false>, a, b, p));
     }
   } else {
     const int grid = std::min(p.num_tiles, num_sms());
-    tc_fast_kernel<OP, false><<<grid, kThreads, smem, state().stream>>>(a, b, p);
+    tc_fast_kernel<OP, false, XM><<<grid, kThreads, smem, state().stream>>>(a, b, p);
   }
   count_launch();
   CNB_LAUNCH_CHECK("tc_fast");
@@ -1402,6 +1465,25 @@ static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float*
       if (ok) { launch_fast<kFprop>(fa, fb, f); done = true; }
     }
   }
+  // tf32 x mode (RGB first layer) on the lean kernel: one k-block per channel = 8 x 8 taps
+  if (!done && !bf && x_mode && fast_enabled() && p.a_merged && p.splits == 1 && st == 0.f && !p.cta2 && g.Cout % 32 == 0 &&
+      p.BN % 32 == 0) {
+    TcParams f = p;
+    f.ksteps = 8; f.a_stage_bytes = 32768; f.b_rows = 2 * p.BN; f.b_tx_bytes = (uint32_t)f.b_rows * 128;
+    int stages = kMaxStages;
+    while (stages > 1 && fast_smem_bytes(f.a_stage_bytes, (size_t)f.b_rows * 128, stages) > 225 * 1024) stages--;
+    f.stages = stages;
+    const long long N = g.N;
+    const long long adims[5] = {32, g.W, g.H, N / 32, g.Cin}, astr[4] = {N, N * g.W, 32, N * g.W * g.H};
+    const int abox[5] = {32, 8, 8, 4, 1};
+    const long long bdims[5] = {32, g.kx, g.ky, g.Cout / 32, g.Cin}, bstr[4] = {g.Cout, (long long)g.Cout * g.kx, 32, (long long)g.Cout * taps};
+    const int bbox[5] = {32, 8, 8, p.BN / 32, 1};
+    CUtensorMap fa, fb;
+    if (stages >= 2 && make_map(&fa, img, e, 5, adims, astr, abox, true) && make_map(&fb, flt, e, 5, bdims, bstr, bbox, true)) {
+      launch_fast<kFprop, true>(fa, fb, f);
+      done = true;
+    }
+  }
   if (!done) launch<kFprop>(ma, mb, p);
   if (emit && fuse.emitted) *fuse.emitted = true;
   if (p.splits > 1) reduce_split((const float*)ws, out, out_elems, p.splits, st, so, bias, (long long)g.modules * g.N, fuse.relu, nullptr);
@@ -1605,7 +1687,22 @@ static bool tc_conv_outp_impl(const ConvGeom& g, const float* images, const floa
   }
   const int units = g.modY * g.frames;               // reduction units = module rows
   const long long base_tiles = (long long)(x_mode ? 1 : p.taps) * p.m_tiles * p.n_tiles;
-  int splits = (int)std::max<long long>(1, std::min<long long>(units, (2LL * num_sms()) / base_tiles));
+  // reduction splits: the count that minimises (waves of the persistent grid) x (work of one tile), where a tile costs its
+  // module rows plus an epilogue worth ~1 row; the old rule (fill 2 waves) left e.g. 168 pair tiles for 74 pair slots
+  int splits;
+  {
+    const bool may_pair = pair_enabled() && !x_mode && p.m_tiles >= 2 && (p.m_tiles & 1) == 0;
+    const long long slots = may_pair ? num_sms() / 2 : num_sms();
+    const long long base = may_pair ? base_tiles / 2 : base_tiles;
+    const int cap = (int)std::max<long long>(1, std::min<long long>(units, (3LL * num_sms()) / std::max<long long>(base_tiles, 1)));
+    double best = 1e30; splits = 1;
+    for (int sp = 1; sp <= cap; sp++) {
+      const int ups = ceil_div(units, sp), real = ceil_div(units, ups);
+      const long long waves = ceil_div<long long>(base * real, slots);
+      const double cost = (double)waves * (ups + 1.0) + 0.02 * real;        // + the partial-sum traffic of each extra split
+      if (cost < best - 1e-9) { best = cost; splits = real; }
+    }
+  }
   const long long elems = (long long)g.Cout * g.K;
   while (splits > 1 && elems * splits * 4 > (1LL << 30)) splits--;
   p.units_per_split = ceil_div(units, splits);
@@ -1659,6 +1756,27 @@ static bool tc_conv_outp_impl(const ConvGeom& g, const float* images, const floa
         launch_fast<kWgrad>(fa, fb, f);
         done = true;
       }
+    }
+  }
+  if (!done && !bf && x_mode && fast_enabled() && g.frames == 1 && g.N % 64 == 0 && !p.cta2 && (p.splits > 1 || st == 0.f)) {
+    TcParams f = p;
+    if (p.splits > 1) f.so = 1.f;
+    const int cps = 2, rows_panel = p.x_ct * g.ky * 8;             // 64 images per stage; tap rows of one 32-image panel
+    f.ksteps = 4 * cps; f.a_stage_bytes = 16384u * cps;
+    f.b_rows = rows_panel * cps + 8;                               // the MMA reads BN >= rows_panel rows of the last panel
+    f.b_tx_bytes = (uint32_t)(rows_panel * cps) * 128;
+    int stages = kMaxStages;
+    while (stages > 1 && fast_smem_bytes(f.a_stage_bytes, (size_t)f.b_rows * 128, stages) > 225 * 1024) stages--;
+    f.stages = stages;
+    const long long N = g.N;
+    const long long adims[5] = {32, g.modX, g.modY, g.Cout, N / 32}, astr[4] = {N, N * g.modX, N * g.modX * g.modY, 32};
+    const int abox[5] = {32, 1, 1, BM, cps};
+    const long long bdims[5] = {32, g.W, g.H, g.Cin, N / 32}, bstr[4] = {N, N * g.W, N * g.W * g.H, 32};
+    const int bbox[5] = {32, 8, g.ky, p.x_ct, cps};
+    CUtensorMap fa, fb;
+    if (stages >= 2 && make_map(&fa, der, e, 5, adims, astr, abox, false) && make_map(&fb, img, e, 5, bdims, bstr, bbox, false)) {
+      launch_fast<kWgrad, true>(fa, fb, f);
+      done = true;
     }
   }
   if (!done) launch<kWgrad>(ma, mb, p);

@@ -201,6 +201,9 @@ class FCEdge : public EdgeWithWeight {          // weights [Cout x K] column-maj
   int FanIn() const override { return num_inputs_; }
   bool CanFuseReLU() const override { return !has_no_bias_; }
   bool CanFuseMask() const override { return true; }
+  // the FC dgrad sees its input flattened to (N, 1, 1, pixels*channels): its column sums are per (pixel, channel), which is
+  // the bias gradient of the edge below only when that layer has a single pixel
+  bool CanProduceBiasGrad() const override { return image_size_y_ * image_size_x_ * image_size_t_ == 1; }
 
  private:
   void View(Matrix& in, Matrix& out);
