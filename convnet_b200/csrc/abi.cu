@@ -50,6 +50,7 @@ void conv_up(const ConvGeom& g, const float* images, const float* filters, float
 
 void conv_down(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float st, float so) {
   Fuse fuse = take_fuse();
+  so *= fuse.out_scale;
   // the mask can ride in the epilogue only when one launch produces the final value of every target element
   const bool whole = g.conv && g.frames == 1 && g.cin0 == 0 && g.Cin == g.CinT;
   const float* late_mask = nullptr;

@@ -648,8 +648,12 @@ struct FastTile {
 
 // XM: the tf32 "x mode" for tiny channel counts (the RGB first layer), see TcParams::x_mode — fprop: one k-block per
 // channel = 8 x-taps x 8 filter rows (64 K rows, eight UMMA steps of 8); wgrad: the N tile is (channels x ky rows x 8 taps).
+// 10 warps: producer, MMA issuer, and EIGHT epilogue warps — two per TMEM lane quarter, taking alternate 32-column slabs.
+// With the main loop no longer the limiter the 1x1 layers became epilogue-bound at ~2.5 TB/s: one warp per scheduler
+// cannot keep enough stores / mask loads in flight (profiles/r2_layer_probe_fast_v2_dgrad_as_fprop.log).
+constexpr int kFastThreads = 320;
 template <int OP, bool PAIR, bool XM>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kFastThreads, 1)
 tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB, const __grid_constant__ TcParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -662,7 +666,7 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; s++) { ptx::mbar_init(&ctl->full[s], 1); ptx::mbar_init(&ctl->empty[s], 1); }
-    for (int a = 0; a < 2; a++) { ptx::mbar_init(&ctl->tmem_full[a], 1); ptx::mbar_init(&ctl->tmem_empty[a], PAIR ? 8 : 4); }
+    for (int a = 0; a < 2; a++) { ptx::mbar_init(&ctl->tmem_full[a], 1); ptx::mbar_init(&ctl->tmem_empty[a], PAIR ? 16 : 8); }
     ptx::fence_barrier_init();
     ptx::tma_prefetch_desc(&mapA);
     ptx::tma_prefetch_desc(&mapB);
@@ -911,7 +915,8 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
     }
   } else if (warp >= 2) {
     // =============================== epilogue ===================================
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;                      // TMEM lane quarter this warp may read (warp id mod 4)
+    const int slab0 = ((warp - 2) >> 2) * 32;            // warps 2-5 take slabs 0, 2, 4, ...; warps 6-9 slabs 1, 3, 5, ...
     uint32_t acc = 0, acc_phase = 0;
     const uint32_t tfull0 = ptx::smem_u32(&ctl->tmem_full[0]), tempty0 = ptx::smem_u32(&ctl->tmem_empty[0]);
     for (int t = t_first; t < p.num_tiles; t += t_step) {
@@ -958,7 +963,7 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
       ptx::mbar_wait_a(tfull0 + acc * 8, acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_addr = tmem_base + ((uint32_t)(quarter * 32) << 16) + acc * (uint32_t)p.BN;
-      for (int j0 = 0; j0 < ncols; j0 += 32) {                       // ncols is a multiple of 32 (host)
+      for (int j0 = slab0; j0 < ncols; j0 += 64) {                   // ncols is a multiple of 32 (host)
         float v[32];
         ptx::tmem_ld_32x32(t_addr + j0, v);
         ptx::tmem_ld_wait();
@@ -1203,7 +1208,7 @@ void launch_fast(const CUtensorMap& a, const CUtensorMap& b, TcParams& p) {
     if constexpr (!XM) {
       cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(2u * (unsigned)std::min(p.num_tiles, num_sms() / 2));
-      cfg.blockDim = dim3(kThreads);
+      cfg.blockDim = dim3(kFastThreads);
       cfg.dynamicSmemBytes = smem;
       cfg.stream = state().stream;
       cudaLaunchAttribute attr[1];
@@ -1214,7 +1219,7 @@ void launch_fast(const CUtensorMap& a, const CUtensorMap& b, TcParams& p) {
     }
   } else {
     const int grid = std::min(p.num_tiles, num_sms());
-    tc_fast_kernel<OP, false, XM><<<grid, kThreads, smem, state().stream>>>(a, b, p);
+    tc_fast_kernel<OP, false, XM><<<grid, kFastThreads, smem, state().stream>>>(a, b, p);
   }
   count_launch();
   CNB_LAUNCH_CHECK("tc_fast");
@@ -1687,19 +1692,22 @@ static bool tc_conv_outp_impl(const ConvGeom& g, const float* images, const floa
   }
   const int units = g.modY * g.frames;               // reduction units = module rows
   const long long base_tiles = (long long)(x_mode ? 1 : p.taps) * p.m_tiles * p.n_tiles;
-  // reduction splits: the count that minimises (waves of the persistent grid) x (work of one tile), where a tile costs its
-  // module rows plus an epilogue worth ~1 row; the old rule (fill 2 waves) left e.g. 168 pair tiles for 74 pair slots
+  // reduction splits: minimise  waves x (rows per tile x time of a row + epilogue)  +  the partial-sum reduction pass.
+  // (The old rule — fill two waves — left e.g. 168 pair tiles for 74 pair slots.)  Times in microseconds, coarse: one
+  // k-block ~0.3 us, a tile epilogue ~1.5 us, the reduction streams (splits + 1) x |dW| floats at ~5 TB/s.
   int splits;
   {
     const bool may_pair = pair_enabled() && !x_mode && p.m_tiles >= 2 && (p.m_tiles & 1) == 0;
     const long long slots = may_pair ? num_sms() / 2 : num_sms();
     const long long base = may_pair ? base_tiles / 2 : base_tiles;
-    const int cap = (int)std::max<long long>(1, std::min<long long>(units, (3LL * num_sms()) / std::max<long long>(base_tiles, 1)));
+    const double row_us = 0.3 * g.modX * std::max(1, p.nbc / 2);
+    const double dw_bytes = 4.0 * g.Cout * g.K;
+    const int cap = (int)std::max<long long>(1, std::min<long long>(units, (4LL * num_sms()) / std::max<long long>(base_tiles, 1)));
     double best = 1e30; splits = 1;
     for (int sp = 1; sp <= cap; sp++) {
       const int ups = ceil_div(units, sp), real = ceil_div(units, ups);
       const long long waves = ceil_div<long long>(base * real, slots);
-      const double cost = (double)waves * (ups + 1.0) + 0.02 * real;        // + the partial-sum traffic of each extra split
+      const double cost = (double)waves * (ups * row_us + 1.5) + (real > 1 ? dw_bytes * (real + 1) / 5e6 : 0.0);
       if (cost < best - 1e-9) { best = cost; splits = real; }
     }
   }

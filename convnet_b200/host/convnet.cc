@@ -75,6 +75,7 @@ void Layer::ApplyDropout(bool train, unsigned long long step, unsigned long long
 }
 void Layer::ApplyDerivativeofDropout(bool emit) {
   if (config_.dropprob <= 0 || config_.is_input) return;
+  if (dropout_deriv_folded_) { dropout_deriv_folded_ = false; return; }    // the dgrad above already applied 1/(1-p) * [state > 0]
   if (emit) convnet_b200_emit_bf16_next();
   cnb_mult(deriv_.GetDevData(), dropout_mask_.GetDevData(), (long long)deriv_.GetNumEls());
 }
@@ -267,6 +268,7 @@ void ConvNet::AllocateMemory() {
 
 void ConvNet::Fprop(bool train) {                            // convnet.cc:377-388
   const bool bf16 = convnet_b200_get_conv_precision() == 2;
+  dropout_active_ = train;
   for (size_t i = 1; i < layers_.size(); i++) {
     Layer* l = layers_[i];
     Edge* e = edges_[i - 1];
@@ -317,10 +319,16 @@ void ConvNet::Bprop() {                                      // convnet.cc:390-4
         }
     if (!in->IsInput()) {
       const bool want_in = bf16 && i >= 2 && edges_[i - 2]->WantsBf16Deriv();
-      e->SetEmitDown(want_in && !in->HasDropout() && !in->HasSeparateDerivPass());
+      // dropout derivative of a ReLU layer = one factor on the kept units, which the fused mask already selects
+      static const bool no_fold = getenv("CONVNET_B200_NO_DROPOUT_FOLD") && getenv("CONVNET_B200_NO_DROPOUT_FOLD")[0] == '1';
+      const bool fold = !no_fold && dropout_active_ && in->HasDropout() && in->GetActivation() == RECTIFIED_LINEAR &&
+                        !in->HasSeparateDerivPass() && e->CanScaleDeriv();
+      if (fold) { e->SetDerivScale(in->DropoutScale()); in->SetDropoutDerivFolded(true); }
+      const bool drop_pass = in->HasDropout() && !fold;
+      e->SetEmitDown(want_in && !drop_pass && !in->HasSeparateDerivPass());
       // the kernel that writes in's derivative LAST can also sum its channels: that is the bias gradient of the edge below
       static const bool no_bg = getenv("CONVNET_B200_NO_FUSED_BIAS_GRAD") && getenv("CONVNET_B200_NO_FUSED_BIAS_GRAD")[0] == '1';
-      if (!no_bg && i >= 2 && e->CanProduceBiasGrad() && !in->HasDropout() && !in->HasSeparateDerivPass()) {
+      if (!no_bg && i >= 2 && e->CanProduceBiasGrad() && !drop_pass && !in->HasSeparateDerivPass()) {
         Edge::BiasGradTarget t;
         if (edges_[i - 2]->OfferFusedBiasGrad(&t)) e->SetBiasGradRequest(t);
       }

@@ -44,6 +44,8 @@ class Layer {                                   // src/layer.{h,cc}, reduced to 
   void ApplyDropout(bool train, unsigned long long step, unsigned long long salt, bool emit_bf16 = false);   // layer.cc:  mask = rand > dropprob ; state *= mask
   void ApplyDerivativeofDropout(bool emit_bf16 = false);
   bool HasDropout() const { return config_.dropprob > 0 && !config_.is_input; }
+  float DropoutScale() const { return 1.0f / (1.0f - config_.dropprob); }
+  void SetDropoutDerivFolded(bool v) { dropout_deriv_folded_ = v; }   // this step: the edge above scaled the derivative instead
   bool HasSeparateActivationPass() const { return config_.activation == RECTIFIED_LINEAR && !activation_fused_; }
   bool HasSeparateDerivPass() const { return config_.activation == RECTIFIED_LINEAR && !deriv_fused_; }
   void ComputeDeriv();                          // softmax + cross-entropy: deriv = p - onehot   (loss_functions.cc)
@@ -68,7 +70,7 @@ class Layer {                                   // src/layer.{h,cc}, reduced to 
   int image_size_y_, image_size_x_, image_size_t_;
   Matrix state_, deriv_, loss_per_image_, dropout_mask_;
   int* labels_ = nullptr;
-  bool activation_fused_ = false, deriv_fused_ = false;
+  bool activation_fused_ = false, deriv_fused_ = false, dropout_deriv_folded_ = false;
 };
 
 // NCCL all-reduce of the flat gradient buffer, bucketed along edge boundaries and launched on a side
@@ -150,6 +152,7 @@ class ConvNet {
   cudaStream_t side_ = nullptr;
   cudaEvent_t ev_main_ = nullptr, ev_side_ = nullptr;
   bool eager_update_ = false, side_pending_ = false, updated_in_bprop_ = false;
+  bool dropout_active_ = false;                 // the last Fprop applied dropout (train == true): states hold relu(x) * mask
   unsigned long long step_ = 0;
   unsigned long long dropout_salt_ = 0xD1B54A32D192ED03ULL;      // model seed and data-parallel rank, see SetDataParallel
 };

@@ -101,6 +101,10 @@ class Edge {
   struct BiasGradTarget { float* grad_bias = nullptr; float st = 0.f, so = 1.f; };
   virtual bool OfferFusedBiasGrad(BiasGradTarget*) { return false; }
   void SetBiasGradRequest(const BiasGradTarget& t) { bg_request_ = t; }
+  // ComputeDown multiplies the derivative it writes by this factor (1 = none): the dropout derivative of a ReLU layer folded
+  // into the dgrad epilogue (convnet_b200_fuse_next_scale); only edges whose ComputeDown is a conv dgrad with the mask fused
+  void SetDerivScale(float s) { deriv_scale_ = s; }
+  virtual bool CanScaleDeriv() const { return false; }
   virtual bool CanProduceBiasGrad() const { return false; }   // ComputeDown kernels that take the request
   virtual bool WantsBf16Input() const { return false; }      // this edge reads its input (fprop / wgrad) as bf16
   virtual bool WantsBf16Deriv() const { return false; }      // this edge reads its output derivative (wgrad / dgrad) as bf16
@@ -116,9 +120,12 @@ class Edge {
   bool fuse_relu_ = false, fuse_mask_ = false;
   bool emit_up_ = false, emit_down_ = false;
   BiasGradTarget bg_request_;
+  float deriv_scale_ = 1.f;
   void ApplyBiasGradRequest() {            // call right before the ComputeDown kernel
     if (bg_request_.grad_bias) convnet_b200_fuse_next_bias_grad(bg_request_.grad_bias, bg_request_.st, bg_request_.so);
     bg_request_ = BiasGradTarget();
+    if (deriv_scale_ != 1.f) convnet_b200_fuse_next_scale(deriv_scale_);
+    deriv_scale_ = 1.f;
   }
 };
 
@@ -148,6 +155,7 @@ class EdgeWithWeight : public Edge {
   bool OfferFusedBiasGrad(BiasGradTarget* t) override;
   virtual bool BiasIsPerChannel2D() const { return !has_no_bias_; }       // one bias per output channel, 2-D layer
   bool CanProduceBiasGrad() const override { return true; }
+  bool CanScaleDeriv() const override { return fuse_mask_; }               // (3-D ConvEdge: fuse_mask_ is off, CanFuseMask)
 
  protected:
   void StageForUp(Matrix& input);

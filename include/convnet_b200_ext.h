@@ -49,6 +49,12 @@ void convnet_b200_reset_launch_count(void);
  * kernel), so the separate pass over the derivative disappears; calls that cannot do it run that pass themselves. */
 void convnet_b200_fuse_next_bias_grad(float* grad_bias, float scaleTargets, float scaleOutput);
 
+/* One-shot: the NEXT convDown* call multiplies its result by `scale` (before the relu_mask of convnet_b200_fuse_next).
+ * This is how the derivative of inverted dropout disappears as a pass: for a ReLU layer with dropout the state holds
+ * relu(x) * m with m in {0, 1/(1-p)}, so  deriv * m * [state > 0]  (Layer::ApplyDerivativeofDropout followed by
+ * ApplyDerivativeOfActivation, src/layer.cc:367-395,562-580)  ==  deriv * 1/(1-p) * [state > 0]. */
+void convnet_b200_fuse_next_scale(float scale);
+
 /* The conv kernels are persistent: one CTA (or CTA pair) per SM, each owning most of the SM's shared memory.  A kernel
  * of another library that must run CONCURRENTLY (an NCCL collective on a side stream) cannot co-reside with them and
  * would otherwise wait for — or push out — a whole wave.  convnet_b200_reserve_sms(n) makes the persistent grids leave
