@@ -1,6 +1,8 @@
 // abi.cu — the extern "C" surface: ABI-1 (include/convnet_b200_conv_gemm.h, the
 // reference's cudamat_conv_gemm.cuh) and ABI-2 (include/convnet_b200_conv.h, the
 // reference's cudamat_conv.cuh), both on the same kernels.
+#include <nvtx3/nvToolsExt.h>
+
 #include <algorithm>
 
 #include "../../include/convnet_b200_conv.h"
@@ -13,6 +15,13 @@ using namespace cnb;
 namespace {
 
 ConvDesc as_2d(ConvDesc d) { d.kernel_size_t = 1; d.stride_t = 1; d.padding_t = 0; return d; }
+
+// one NVTX range per C-ABI entry (named after the entry point), so an nsys / ncu timeline of a host application shows
+// which reference call every kernel belongs to; header-only NVTX3: a no-op costing a few ns when no tool is attached
+struct Range {
+  explicit Range(const char* name) { nvtxRangePushA(name); }
+  ~Range() { nvtxRangePop(); }
+};
 
 // ---- dispatch: tensor-core path when the mode and the shape allow, else fp32 CUDA cores
 // Writer protocol (stage.cu): drop staged bf16 copies overlapping the target; when the caller asked for a fresh copy
@@ -96,22 +105,26 @@ void conv_outp(const ConvGeom& g, const float* images, const float* derivs, floa
 
 void do_conv_up(const char* what, cudamat* images, cudamat* filters, cudamat* targets, Shape4D* is, Shape4D* fs,
                 Shape4D* ts, ConvDesc d, float st, bool conv) {
+  Range nvtx_range(what);
   ConvGeom g = conv_geom(*is, *fs, *ts, images, filters, targets, d, conv, what);
   conv_up(g, images->data_device, filters->data_device, targets->data_device, st, 1.f);
 }
 void do_conv_down(const char* what, cudamat* derivs, cudamat* filters, cudamat* targets, Shape4D* ds, Shape4D* fs,
                   Shape4D* ts, ConvDesc d, float st, bool conv) {
+  Range nvtx_range(what);
   ConvGeom g = conv_geom(*ts, *fs, *ds, targets, filters, derivs, d, conv, what);
   conv_down(g, derivs->data_device, filters->data_device, targets->data_device, st, 1.f);
 }
 void do_conv_outp(const char* what, cudamat* images, cudamat* derivs, cudamat* targets, Shape4D* is, Shape4D* ds,
                   Shape4D* ts, ConvDesc d, float st, float so, bool conv) {
+  Range nvtx_range(what);
   ConvGeom g = conv_geom(*is, *ts, *ds, images, targets, derivs, d, conv, what);
   conv_outp(g, images->data_device, derivs->data_device, targets->data_device, st, so);
 }
 
 void do_pool(const char* what, bool is_max, cudamat* images, cudamat* targets, Shape4D* is, Shape4D* ts, ConvDesc d,
              float so) {
+  Range nvtx_range(what);
   PoolGeom g = pool_geom(*is, *ts, images, targets, d, what);
   const Fuse fuse = take_fuse();
   Emit emit(targets->data_device, (long long)targets->size[0] * targets->size[1], fuse.emit_bf16 != 0);
@@ -120,6 +133,7 @@ void do_pool(const char* what, bool is_max, cudamat* images, cudamat* targets, S
 }
 void do_max_undo(const char* what, cudamat* images, cudamat* maxGrads, cudamat* maxActs, cudamat* targets,
                  Shape4D* is, Shape4D* gs, ConvDesc d, float st) {
+  Range nvtx_range(what);
   PoolGeom g = pool_geom(*is, *gs, images, maxGrads, d, what);
   CNB_REQUIRE(targets->size[0] == g.N && targets->size[1] == images->size[1], what);
   CNB_REQUIRE(maxActs->size[0] == g.N && maxActs->size[1] == maxGrads->size[1], what);
@@ -134,6 +148,7 @@ void do_max_undo(const char* what, cudamat* images, cudamat* maxGrads, cudamat* 
 }
 void do_avg_undo(const char* what, cudamat* avgGrads, cudamat* targets, Shape4D* gs, Shape4D* ts, ConvDesc d, float st,
                  float so) {
+  Range nvtx_range(what);
   PoolGeom g = pool_geom(*ts, *gs, targets, avgGrads, d, what);
   const Fuse fuse = take_fuse();
   Emit emit(targets->data_device, (long long)targets->size[0] * targets->size[1], fuse.emit_bf16 != 0);
@@ -159,6 +174,7 @@ ConvDesc sample_desc(Shape4D* is, Shape4D* ts, int factor) {      // gemm.cu:150
 
 void do_rnorm(const char* what, cudamat* images, cudamat* targets, int F, int sizeF, float a, float b, bool blocked,
               int frames) {
+  Range nvtx_range(what);
   CNB_REQUIRE(F > 0 && frames > 0, what);
   const long long els = (long long)images->size[0] * images->size[1];
   CNB_REQUIRE(els % ((long long)F * frames) == 0, what);
@@ -178,6 +194,7 @@ void do_rnorm(const char* what, cudamat* images, cudamat* targets, int F, int si
 }
 void do_rnorm_undo(const char* what, cudamat* outGrads, cudamat* inputs, cudamat* targets, int F, int sizeF, float a,
                    float b, bool blocked, int frames) {
+  Range nvtx_range(what);
   CNB_REQUIRE(F > 0 && frames > 0, what);
   const long long els = (long long)inputs->size[0] * inputs->size[1];
   CNB_REQUIRE(els % ((long long)F * frames) == 0, what);

@@ -258,11 +258,30 @@ void cnb_add_channel_bias_relu(float* acts, const float* bias, long long rows, i
   bias_launch<true>(acts, bias, rows, cols);
   end_write(acts, rows * cols, emit, nullptr);
 }
+// partial sums of the bias gradient live in their OWN scratch, not in the shared workspace: a host may run this pass on a
+// side stream beside conv kernels that are using the workspace (host/convnet.cc does)
+static float* colsum_scratch(size_t floats) {
+  static float* buf = nullptr; static size_t cap = 0; static int dev = -1;
+  const int cur = current_device();
+  if (buf && (cap < floats || dev != cur)) {
+    CNB_CUDA_CHECK(cudaDeviceSynchronize());
+    if (dev != cur) CNB_CUDA_CHECK(cudaSetDevice(dev));
+    CNB_CUDA_CHECK(cudaFree(buf));
+    if (dev != cur) CNB_CUDA_CHECK(cudaSetDevice(cur));
+    buf = nullptr; cap = 0;
+  }
+  if (!buf) {
+    const size_t want = std::max<size_t>(floats, (size_t)1 << 18);
+    CNB_CUDA_CHECK(cudaMalloc((void**)&buf, want * sizeof(float)));
+    cap = want; dev = cur;
+  }
+  return buf;
+}
 void cnb_channel_bias_grad(const float* derivs, float* grad_bias, long long rows, int cols, float st, float so) {
   if (cols <= 0) return;
   int slices = (int)std::max<long long>(1, std::min<long long>(64, (4LL * num_sms()) / cols));
   slices = (int)std::min<long long>(slices, std::max<long long>(1, rows / 1024));
-  float* part = (float*)workspace(sizeof(float) * (size_t)slices * cols);
+  float* part = colsum_scratch((size_t)slices * cols);
   colsum_partial_kernel<<<dim3(cols, slices), 256, 0, state().stream>>>(derivs, part, rows, cols, slices);
   colsum_final_kernel<<<ceil_div(cols, 128), 128, 0, state().stream>>>(part, grad_bias, cols, slices, st, so);
   count_launch(2);

@@ -121,19 +121,25 @@ Staged* acquire_slot(const float* ptr, long long n, int kind = 0) {
 //   bank(a,b)[c + Cin*((u' + ku*v') + ku*kv*o)] = w[o, tx = ra + sx*(ku-1-u'), ty = rb + sy*(kv-1-v'), c]
 // (reference semantics: cudamat_conv_gemm.cu:684-825, convDown = Sgemm + kContract).  The banks are a permutation of the
 // filter tensor (every tap belongs to exactly one phase), built by one small kernel and cached like a bf16 copy.
+// one 32 x 32 (o, c) tile of one tap per block: coalesced reads along o, coalesced writes along c
 __global__ void __launch_bounds__(256) dgrad_bank_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ out, DgradBanks b,
                                                          int Cin, int Cout, int kx, int ky, int sx, int sy) {
-  const long long total = (long long)Cin * Cout * kx * ky;
-  for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total; idx += (long long)gridDim.x * blockDim.x) {
-    int ph = 0;
-    while (ph + 1 < b.count && idx >= b.phase[ph + 1].offset) ph++;
-    const DgradPhase& P = b.phase[ph];
-    const long long l = idx - P.offset;
-    const int T = P.ku * P.kv;
-    const int c = (int)(l % Cin), t = (int)((l / Cin) % T), o = (int)(l / ((long long)Cin * T));
-    const int u = t % P.ku, v = t / P.ku;
-    const int tx = P.rx + sx * (P.ku - 1 - u), ty = P.ry + sy * (P.kv - 1 - v);
-    out[idx] = __float2bfloat16_rn(w[o + (long long)Cout * (tx + kx * (ty + ky * c))]);
+  __shared__ float tile[32][33];
+  int z = blockIdx.z, ph = 0;                         // z enumerates (phase, tap'') in bank order
+  while (z >= b.phase[ph].ku * b.phase[ph].kv) { z -= b.phase[ph].ku * b.phase[ph].kv; ph++; }
+  const DgradPhase& P = b.phase[ph];
+  const int T = P.ku * P.kv, u = z % P.ku, v = z / P.ku;
+  const int tx = P.rx + sx * (P.ku - 1 - u), ty = P.ry + sy * (P.kv - 1 - v);
+  const int o0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+  const int lx = threadIdx.x & 31, ly = threadIdx.x >> 5;         // 32 x 8 threads
+  for (int r = ly; r < 32; r += 8) {
+    const int c = c0 + r, o = o0 + lx;
+    tile[r][lx] = (c < Cin && o < Cout) ? w[o + (long long)Cout * (tx + kx * (ty + ky * c))] : 0.f;
+  }
+  __syncthreads();
+  for (int r = ly; r < 32; r += 8) {
+    const int o = o0 + r, c = c0 + lx;
+    if (o < Cout && c < Cin) out[P.offset + c + (long long)Cin * (z + (long long)T * o)] = __float2bfloat16_rn(tile[lx][r]);
   }
 }
 
@@ -170,7 +176,7 @@ const __nv_bfloat16* dgrad_weights(const float* filters, const ConvGeom& g, cons
   Staged* e = find_slot(filters, dev, 1);
   if (e && e->valid && e->n == n && e->sig == sig) { e->tick = ++g_tick; return e->buf; }
   e = acquire_slot(filters, n, 1);
-  const int grid = (int)std::min<long long>(std::max<long long>(ceil_div<long long>(n, 256), 1), 8LL * num_sms());
+  const dim3 grid((unsigned)ceil_div(g.Cout, 32), (unsigned)ceil_div(g.Cin, 32), (unsigned)(g.kx * g.ky));
   dgrad_bank_kernel<<<grid, 256, 0, state().stream>>>(filters, e->buf, b, g.Cin, g.Cout, g.kx, g.ky, g.sx, g.sy);
   count_launch();
   CNB_LAUNCH_CHECK("dgrad_banks");

@@ -225,6 +225,7 @@ ConvNet::~ConvNet() {
   if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); }
   if (ev_main_) cudaEventDestroy(ev_main_);
   if (ev_side_) cudaEventDestroy(ev_side_);
+  if (lane_.ready) cudaEventDestroy(lane_.ready);
   convnet_b200_reserve_sms(0);
   convnet_b200_bf16_invalidate(nullptr);                     // the buffers go away; a later net may get the same addresses
   for (Edge* e : edges_) delete e;
@@ -264,6 +265,13 @@ void ConvNet::AllocateMemory() {
   HOST_CUDA_CHECK(cudaEventCreateWithFlags(&ev_main_, cudaEventDisableTiming));
   HOST_CUDA_CHECK(cudaEventCreateWithFlags(&ev_side_, cudaEventDisableTiming));
   SetBucketFloats((size_t)8 << 20);
+  static const bool no_lane = getenv("CONVNET_B200_NO_SIDE_BIAS_GRAD") && getenv("CONVNET_B200_NO_SIDE_BIAS_GRAD")[0] == '1';
+  if (!no_lane) {
+    lane_.stream = side_;
+    HOST_CUDA_CHECK(cudaEventCreateWithFlags(&lane_.ready, cudaEventDisableTiming));
+    for (Edge* e : edges_)
+      if (EdgeWithWeight* w = dynamic_cast<EdgeWithWeight*>(e)) w->SetSideLane(&lane_);
+  }
 }
 
 void ConvNet::Fprop(bool train) {                            // convnet.cc:377-388
@@ -339,6 +347,7 @@ void ConvNet::Bprop() {                                      // convnet.cc:390-4
       for (const Bucket& b : buckets_)
         if (b.trigger == i - 1) IssueBucketUpdate(b);
   }
+  if (!eager_update_ && !(dp_ && dp_->world() > 1)) WaitSide();   // stand-alone Bprop: the gradients are complete on return
 }
 
 // the SGD step of one bucket on the side stream, after (stream order) that bucket's all-reduce and after (event) the
@@ -357,6 +366,7 @@ void ConvNet::IssueBucketUpdate(const Bucket& b) {
   side_pending_ = true;
 }
 void ConvNet::WaitSide() {
+  if (lane_.used) { side_pending_ = true; lane_.used = false; }
   if (!side_pending_) return;
   HOST_CUDA_CHECK(cudaEventRecord(ev_side_, side_));
   HOST_CUDA_CHECK(cudaStreamWaitEvent(Matrix::Stream(), ev_side_, 0));

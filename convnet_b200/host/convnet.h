@@ -151,6 +151,7 @@ class ConvNet {
   std::vector<Bucket> buckets_;
   cudaStream_t side_ = nullptr;
   cudaEvent_t ev_main_ = nullptr, ev_side_ = nullptr;
+  SideLane lane_;                               // what the edges see of the side stream (bias-gradient passes)
   bool eager_update_ = false, side_pending_ = false, updated_in_bprop_ = false;
   bool dropout_active_ = false;                 // the last Fprop applied dropout (train == true): states hold relu(x) * mask
   unsigned long long step_ = 0;

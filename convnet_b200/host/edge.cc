@@ -81,6 +81,16 @@ void EdgeWithWeight::StageForBprop(Matrix& deriv_output) {
   if (convnet_b200_get_conv_precision() != 2) return;
   if (bf_outer_ == 1 || bf_down_ == 1) convnet_b200_bf16_ensure(deriv_output.GetDevData(), (long long)deriv_output.GetNumEls());
 }
+void EdgeWithWeight::SumBiasRows(Matrix& deriv_output, float scale_targets, float scale) {
+  if (!side_ || !side_->stream) { deriv_output.SumRows(grad_bias_, scale_targets, scale); return; }
+  cudaEventRecord(side_->ready, Matrix::Stream());            // the derivative is final on the main stream
+  cudaStreamWaitEvent(side_->stream, side_->ready, 0);
+  void* main_stream = convnet_b200_get_stream();
+  convnet_b200_set_stream(side_->stream);
+  deriv_output.SumRows(grad_bias_, scale_targets, scale);
+  convnet_b200_set_stream(main_stream);
+  side_->used = true;
+}
 void EdgeWithWeight::NoteUp() { bf_up_ = convnet_b200_last_conv_path() == 2 ? 1 : 0; }
 void EdgeWithWeight::NoteDown() { bf_down_ = convnet_b200_last_conv_path() == 2 ? 1 : 0; }
 void EdgeWithWeight::NoteOuter() { bf_outer_ = convnet_b200_last_conv_path() == 2 ? 1 : 0; }
@@ -238,7 +248,7 @@ void ConvEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {   // :183-245
     if (shared_bias_ && image_size_t_ == 1) {
       // the reference sums in two steps through a temp (:212-218); one deterministic pass here
       deriv_output.Reshape(-1, conv_desc_.num_output_channels);
-      deriv_output.SumRows(grad_bias_, scale_targets, scale);
+      SumBiasRows(deriv_output, scale_targets, scale);
       deriv_output.Reshape(batch_size, -1);
     } else if (shared_bias_) {
       deriv_output.Reshape(-1, conv_desc_.num_output_channels * num_modules_t_);
@@ -329,7 +339,7 @@ void FCEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {                
   NoteOuter();
   const bool bias_done = bias_grad_fused_;
   bias_grad_fused_ = false;
-  if (!has_no_bias_ && !bias_done) deriv_output.SumRows(grad_bias_, scale_targets, scale_gradients_ / batch_size);
+  if (!has_no_bias_ && !bias_done) SumBiasRows(deriv_output, scale_targets, scale_gradients_ / batch_size);
   input.GetShape4D() = si; deriv_output.GetShape4D() = so;
   IncrementNumGradsReceived();
 }
@@ -390,7 +400,7 @@ void ConvOneToOneEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {      
   bias_grad_fused_ = false;
   if (!has_no_bias_ && !bias_done) {
     deriv_output.Reshape(-1, num_output_channels_);
-    deriv_output.SumRows(grad_bias_, scale_targets, scale_gradients_ / batch_size);
+    SumBiasRows(deriv_output, scale_targets, scale_gradients_ / batch_size);
     deriv_output.Reshape(batch_size, -1);
   }
   IncrementNumGradsReceived();

@@ -129,8 +129,14 @@ class Edge {
   }
 };
 
+// The side stream of ConvNet::TrainOneBatch (all-reduce + optimizer, see convnet.h): bias-gradient column sums are
+// memory-bound passes over a derivative that is already final, so they run there, beside the tensor-bound wgrad / dgrad
+// kernels of the main stream.  Null stream: everything stays on the main stream.
+struct SideLane { cudaStream_t stream = nullptr; cudaEvent_t ready = nullptr; bool used = false; };
+
 class EdgeWithWeight : public Edge {
  public:
+  void SetSideLane(SideLane* s) { side_ = s; }
   explicit EdgeWithWeight(const EdgeConfig& c) : Edge(c), has_no_bias_(c.has_no_bias), scale_gradients_(c.scale_gradients), num_grads_received_(0) {}
   bool HasNoParameters() const override { return false; }
   void UpdateWeights() override;                                         // src/edge_with_weight.cc:96-118
@@ -154,12 +160,15 @@ class EdgeWithWeight : public Edge {
   void AppendSgdTensors(std::vector<CnbSgdTensor>& out);                 // weights (+ bias) of this edge for one multi-tensor update
   bool OfferFusedBiasGrad(BiasGradTarget* t) override;
   virtual bool BiasIsPerChannel2D() const { return !has_no_bias_; }       // one bias per output channel, 2-D layer
-  bool CanProduceBiasGrad() const override { return true; }
+  // (a conv dgrad would only run the column-sum pass inside the library call, on the main stream; leaving it to the edge
+  //  below puts it on the side lane instead — so only the pooling edges, whose kernels really fuse it, take the request)
   bool CanScaleDeriv() const override { return fuse_mask_; }               // (3-D ConvEdge: fuse_mask_ is off, CanFuseMask)
 
  protected:
   void StageForUp(Matrix& input);
   void StageForBprop(Matrix& deriv_output);
+  void SumBiasRows(Matrix& deriv_output, float scale_targets, float scale);      // SumRows on the side lane when there is one
+  SideLane* side_ = nullptr;
   void NoteUp();
   void NoteDown();
   void NoteOuter();
@@ -187,7 +196,6 @@ class ConvEdge : public EdgeWithWeight {
   bool CanFuseReLU() const override { return !has_no_bias_ && shared_bias_ && image_size_t_ == 1; }
   bool CanFuseMask() const override { return image_size_t_ == 1; }
   bool BiasIsPerChannel2D() const override { return !has_no_bias_ && shared_bias_ && image_size_t_ == 1; }
-  bool CanProduceBiasGrad() const override { return image_size_t_ == 1; }
 
  private:
   ConvDesc conv_desc_;
@@ -209,9 +217,7 @@ class FCEdge : public EdgeWithWeight {          // weights [Cout x K] column-maj
   int FanIn() const override { return num_inputs_; }
   bool CanFuseReLU() const override { return !has_no_bias_; }
   bool CanFuseMask() const override { return true; }
-  // the FC dgrad sees its input flattened to (N, 1, 1, pixels*channels): its column sums are per (pixel, channel), which is
-  // the bias gradient of the edge below only when that layer has a single pixel
-  bool CanProduceBiasGrad() const override { return image_size_y_ * image_size_x_ * image_size_t_ == 1; }
+
 
  private:
   void View(Matrix& in, Matrix& out);

@@ -115,6 +115,14 @@ ModelConfig BuildGradCheckNet() {
 }
 
 ModelConfig BuildModel(const std::string& name) {
+  // "<model>+gradcheck": the model with run_grad_check's edge flags as BASELINE config 1 states them
+  // (grad_check_num_params: 10, grad_check_epsilon: [1e-2, 1e-3, 1e-4]; src/grad_check.cc:20-61)
+  const std::string suffix = "+gradcheck";
+  if (name.size() > suffix.size() && name.compare(name.size() - suffix.size(), suffix.size(), suffix) == 0) {
+    ModelConfig m = BuildModel(name.substr(0, name.size() - suffix.size()));
+    for (EdgeConfig& e : m.edge) { e.grad_check = true; e.grad_check_num_params = 10; e.grad_check_epsilon = {1e-2f, 1e-3f, 1e-4f}; }
+    return m;
+  }
   if (name == "gradcheck") return BuildGradCheckNet();
   if (name == "alexnet") return BuildAlexNet();
   if (name == "lenet") return BuildLeNet();
