@@ -1675,7 +1675,11 @@ static bool tc_conv_outp_impl(const ConvGeom& g, const float* images, const floa
   const bool x_mode = g.Cin < 8;
   if (x_mode && (g.kx > 8 || g.ky > 8)) return false;
   if (bf && (x_mode || g.N % 8 != 0 || !aligned16(images) || !aligned16(derivs))) return false;
-  if (bf && (long long)g.N * g.modules * g.frames < 1024) return false;      // output-write bound: nothing to gain
+  // few reduction rows (FC layers: K = batch): the call is bound by WRITING dW.  The general kernel gained nothing from bf16
+  // there; the lean one (eight epilogue warps) does, and the operands it converts are tiny — so FC shapes take bf16 only when
+  // they are eligible for it
+  const bool lean_ok = fast_enabled() && !x_mode && g.frames == 1 && g.N % 128 == 0 && g.Cin % 32 == 0;
+  if (bf && (long long)g.N * g.modules * g.frames < 1024 && !lean_ok) return false;
   TcParams p; fill_common(p, g, e);
   p.kc_blocks = 0;
   p.m_tiles = ceil_div(g.Cout, BM);
