@@ -191,7 +191,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e: copy each batch synchronously instead of one step ahead")
-    ap.add_argument("--bucket-mb", type=float, default=32.0, help="gradient all-reduce bucket size")
+    ap.add_argument("--bucket-mb", type=float, default=8.0, help="gradient all-reduce bucket size")
     ap.add_argument("--no-cfg3", action="store_true", help="N > 1: skip the extra 256-images-per-GPU measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)

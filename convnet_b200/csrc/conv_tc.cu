@@ -1345,9 +1345,11 @@ static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float*
   const bool x_mode = g.Cin < 8;                                            // tiny channel counts: taps take the K block
   if (x_mode && (g.kx > 8 || g.ky > 8)) return false;
   if (bf && (x_mode || g.N % 8 != 0 || g.Cout % 8 != 0 || !aligned16(images) || !aligned16(filters))) return false;
-  // few GEMM rows (FC layers at training batch sizes): the call streams the weights once and is HBM-bound on them;
-  // a bf16 staging pass would read them a second time, so such shapes stay on the tf32 path
-  if (bf && (long long)g.N * g.modules * g.frames < 1024) return false;
+  // few GEMM rows (FC layers at training batch sizes): the call streams the weights once and is HBM-bound on them; a bf16
+  // conversion pass inside the call would read them a second time, so such shapes take bf16 only when the caller keeps a
+  // staged bf16 copy of the weights (the training host does: cnb_sgd_momentum refreshes it in the same pass that updates
+  // them) — then the call streams HALF the bytes
+  if (bf && (long long)g.N * g.modules * g.frames < 1024 && !bf16_staged(filters, (long long)g.Cout * g.K)) return false;
   TcParams p; fill_common(p, g, e);
   p.BN = pick_bn(g.Cout, e.chunk);
   static const int bn_override = getenv("CONVNET_B200_FPROP_BN") ? atoi(getenv("CONVNET_B200_FPROP_BN")) : 0;   // experiments
@@ -1584,7 +1586,7 @@ static bool tc_conv_down_impl(const ConvGeom& g, const float* derivs, const floa
   const Elem e = elem_for(bf);
   if (g.N % 4 != 0 || g.Cout % 4 != 0 || g.Cout < 8 || g.Cin < 8) return false;
   if (bf && (g.N % 8 != 0 || g.Cout % 8 != 0 || !aligned16(derivs) || !aligned16(filters))) return false;
-  if (bf && (long long)g.N * g.W * g.H < 1024) return false;                 // weight-streaming bound (see tc_conv_up_impl)
+  if (bf && (long long)g.N * g.W * g.H < 1024 && !bf16_staged(filters, (long long)g.Cout * g.K)) return false;   // see tc_conv_up_impl
   TcParams p; fill_common(p, g, e);
   p.BN = pick_bn(g.Cin, 16);
   p.kc_blocks = ceil_div(g.Cout, e.bk);

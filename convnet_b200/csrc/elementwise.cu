@@ -353,8 +353,9 @@ void cnb_sgd_momentum_multi(const CnbSgdTensor* tensors, int count) {
       t.w = s.w; t.h = s.hist; t.g = s.grad; t.n = s.n; t.lr = s.lr; t.mom = s.momentum; t.l2 = s.l2;
       t.vec = (aligned16(s.w) && aligned16(s.hist) && aligned16(s.grad)) ? 1 : 0;
       // the weights change: a staged bf16 copy of exactly this tensor is refreshed in the same pass, any other overlap dropped
+      const bool had_copy = bf16_staged(s.w, s.n) != nullptr;      // only a copy somebody keeps valid is worth refreshing
       bf16_note_write(s.w, s.n);                    // every derived copy (bf16 twin, dgrad banks) goes stale ...
-      t.w16 = bf16_refresh_slot(s.w, s.n);           // ... and the bf16 twin is re-validated: this kernel rewrites it
+      t.w16 = had_copy ? bf16_refresh_slot(s.w, s.n) : nullptr;    // ... and the bf16 twin is rewritten by this kernel
       b.first_block[b.count] = blocks;
       blocks += (int)ceil_div<long long>(s.n, kSgdChunk);
       b.count++;

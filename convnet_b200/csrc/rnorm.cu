@@ -390,9 +390,14 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_undo_tile_kernel(const float
 // share an SM, else the widest that fits at all; 0 = no tile kernel (window walk with the ring instead)
 static int pick_tile(int F, int arrays, size_t* smem_out) {
   auto bytes = [&](int tl) { return sizeof(float) * ((size_t)arrays * (F + 1) * tl + RN_THREADS); };
-  const size_t two_per_sm = 110 * 1024, one_per_sm = 220 * 1024;
-  for (int tl : {64, 32}) if (bytes(tl) <= two_per_sm) { *smem_out = bytes(tl); return tl; }
-  for (int tl : {64, 32}) if (bytes(tl) <= one_per_sm) { *smem_out = bytes(tl); return tl; }
+  static const int forced = getenv("CONVNET_B200_RNORM_TL") ? atoi(getenv("CONVNET_B200_RNORM_TL")) : 0;     // experiments
+  if ((forced == 32 || forced == 64) && bytes(forced) <= 220 * 1024) { *smem_out = bytes(forced); return forced; }
+  // a CTA works in phases (load everything, scan, compute, store): the loads of one CTA only overlap the arithmetic of
+  // ANOTHER one on the same SM, so prefer the width that leaves room for >= 3 resident CTAs, then 2, then whatever fits
+  const size_t sm = 224 * 1024;
+  for (int per_sm : {3, 2, 1})
+    for (int tl : {64, 32})
+      if (bytes(tl) + 1024 <= sm / per_sm) { *smem_out = bytes(tl); return tl; }
   return 0;
 }
 static bool rn_tile_enabled() {

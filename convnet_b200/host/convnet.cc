@@ -168,11 +168,9 @@ void DataParallelSync::Broadcast(float* buf, size_t count) {
   HOST_CUDA_CHECK(cudaEventRecord(done_, comm_stream_));
   HOST_CUDA_CHECK(cudaStreamWaitEvent(Matrix::Stream(), done_, 0));
 }
-void DataParallelSync::AllReduceAverageAsync(float* buf, size_t offset, size_t count, cudaStream_t side) {
+void DataParallelSync::AllReduceAverageAsync(float* buf, size_t offset, size_t count, cudaStream_t comm) {
   if (world_ <= 1 || count == 0) return;
-  HOST_CUDA_CHECK(cudaEventRecord(ready_, Matrix::Stream()));          // gradients of this bucket are final
-  HOST_CUDA_CHECK(cudaStreamWaitEvent(side, ready_, 0));
-  NCCL_CHECK(nccl().AllReduce(buf + offset, buf + offset, count, ncclFloat, ncclAvg, (ncclComm_t)comm_, side));
+  NCCL_CHECK(nccl().AllReduce(buf + offset, buf + offset, count, ncclFloat, ncclAvg, (ncclComm_t)comm_, comm));
 }
 
 // =================================================================== ConvNet
@@ -222,7 +220,10 @@ ConvNet::ConvNet(const ModelConfig& model, int batch_size) : model_(model), batc
 void ConvNet::InvalidateStaging() { convnet_b200_bf16_invalidate(nullptr); }
 
 ConvNet::~ConvNet() {
+  if (comm_) { cudaStreamSynchronize(comm_); cudaStreamDestroy(comm_); }
   if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); }
+  if (ev_comm_) cudaEventDestroy(ev_comm_);
+  for (cudaEvent_t e : ev_reduced_) cudaEventDestroy(e);
   if (ev_main_) cudaEventDestroy(ev_main_);
   if (ev_side_) cudaEventDestroy(ev_side_);
   if (lane_.ready) cudaEventDestroy(lane_.ready);
@@ -262,6 +263,8 @@ void ConvNet::AllocateMemory() {
   HOST_CUDA_CHECK(cudaStreamSynchronize(Matrix::Stream()));
   InvalidateStaging();
   HOST_CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+  HOST_CUDA_CHECK(cudaStreamCreateWithFlags(&comm_, cudaStreamNonBlocking));
+  HOST_CUDA_CHECK(cudaEventCreateWithFlags(&ev_comm_, cudaEventDisableTiming));
   HOST_CUDA_CHECK(cudaEventCreateWithFlags(&ev_main_, cudaEventDisableTiming));
   HOST_CUDA_CHECK(cudaEventCreateWithFlags(&ev_side_, cudaEventDisableTiming));
   SetBucketFloats((size_t)8 << 20);
@@ -319,12 +322,19 @@ void ConvNet::Bprop() {                                      // convnet.cc:390-4
     e->ComputeOuter(in->GetState(), out->GetDeriv());
     // data parallel: ship every bucket whose last gradient just became final (side stream, overlaps the rest of bprop)
     if (dp_ && dp_->world() > 1)
-      for (const Bucket& b : buckets_)
-        if (b.trigger == i - 1) {
-          if (!side_pending_) convnet_b200_reserve_sms(dp_->reserved_sms());
-          dp_->AllReduceAverageAsync(grad_parameters_.GetDevData(), b.lo, b.hi - b.lo, side_);
-          side_pending_ = true;
-        }
+      for (size_t bi = 0; bi < buckets_.size(); bi++) {
+        const Bucket& b = buckets_[bi];
+        if (b.trigger != i - 1) continue;
+        if (!comm_pending_) convnet_b200_reserve_sms(dp_->reserved_sms());
+        // the bucket's gradients: weight gradients on the main stream, bias gradients (column sums) on the side stream
+        HOST_CUDA_CHECK(cudaEventRecord(ev_main_, Matrix::Stream()));
+        HOST_CUDA_CHECK(cudaStreamWaitEvent(comm_, ev_main_, 0));
+        HOST_CUDA_CHECK(cudaEventRecord(ev_side_, side_));
+        HOST_CUDA_CHECK(cudaStreamWaitEvent(comm_, ev_side_, 0));
+        dp_->AllReduceAverageAsync(grad_parameters_.GetDevData(), b.lo, b.hi - b.lo, comm_);
+        HOST_CUDA_CHECK(cudaEventRecord(ev_reduced_[bi], comm_));
+        comm_pending_ = true;
+      }
     if (!in->IsInput()) {
       const bool want_in = bf16 && i >= 2 && edges_[i - 2]->WantsBf16Deriv();
       // dropout derivative of a ReLU layer = one factor on the kept units, which the fused mask already selects
@@ -344,8 +354,11 @@ void ConvNet::Bprop() {                                      // convnet.cc:390-4
     }
     // the optimizer step of a bucket follows its all-reduce on the side stream once its edges are done with the weights
     if (eager_update_)
-      for (const Bucket& b : buckets_)
-        if (b.trigger == i - 1) IssueBucketUpdate(b);
+      for (size_t bi = 0; bi < buckets_.size(); bi++)
+        if (buckets_[bi].trigger == i - 1) {
+          if (dp_ && dp_->world() > 1) HOST_CUDA_CHECK(cudaStreamWaitEvent(side_, ev_reduced_[bi], 0));   // SGD after its all-reduce
+          IssueBucketUpdate(buckets_[bi]);
+        }
   }
   if (!eager_update_ && !(dp_ && dp_->world() > 1)) WaitSide();   // stand-alone Bprop: the gradients are complete on return
 }
@@ -367,11 +380,16 @@ void ConvNet::IssueBucketUpdate(const Bucket& b) {
 }
 void ConvNet::WaitSide() {
   if (lane_.used) { side_pending_ = true; lane_.used = false; }
+  if (comm_pending_) {                                       // every all-reduce of the step (the SGD steps on side_ wait for theirs too)
+    HOST_CUDA_CHECK(cudaEventRecord(ev_comm_, comm_));
+    HOST_CUDA_CHECK(cudaStreamWaitEvent(Matrix::Stream(), ev_comm_, 0));
+    comm_pending_ = false;
+    convnet_b200_reserve_sms(0);
+  }
   if (!side_pending_) return;
   HOST_CUDA_CHECK(cudaEventRecord(ev_side_, side_));
   HOST_CUDA_CHECK(cudaStreamWaitEvent(Matrix::Stream(), ev_side_, 0));
   side_pending_ = false;
-  convnet_b200_reserve_sms(0);
 }
 
 void ConvNet::UpdateWeights() {                              // convnet.cc:440-450
@@ -425,9 +443,16 @@ void ConvNet::SetDataParallel(DataParallelSync* dp, size_t bucket_floats) {
   dp_ = dp;
   dropout_salt_ = ((unsigned long long)model_.seed * 0xA24BAED4963EE407ULL) ^
                   ((unsigned long long)((dp ? dp->rank() : 0) + 1) * 0xD1B54A32D192ED03ULL);
-  buckets_ = PlanBuckets(edge_offset_, edge_size_, bucket_floats);
+  SetBucketFloats(bucket_floats);
 }
-void ConvNet::SetBucketFloats(size_t bucket_floats) { buckets_ = PlanBuckets(edge_offset_, edge_size_, bucket_floats); }
+void ConvNet::SetBucketFloats(size_t bucket_floats) {
+  buckets_ = PlanBuckets(edge_offset_, edge_size_, bucket_floats);
+  while (ev_reduced_.size() < buckets_.size()) {
+    cudaEvent_t e;
+    HOST_CUDA_CHECK(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    ev_reduced_.push_back(e);
+  }
+}
 void ConvNet::BroadcastParameters() {
   if (dp_) dp_->Broadcast(parameters_.GetDevData(), parameters_.GetNumEls());
   InvalidateStaging();

@@ -84,8 +84,8 @@ class DataParallelSync {
   int world() const { return world_; }
   int rank() const { return rank_; }
   void Broadcast(float* buf, size_t count);                     // initial parameters from rank 0 (convnet.cc:300-309)
-  // average buf[offset, offset+count) over ranks on `side`, ordered after everything already on the compute stream
-  void AllReduceAverageAsync(float* buf, size_t offset, size_t count, cudaStream_t side);
+  // average buf[offset, offset+count) over ranks on `comm` (the caller orders `comm` after the producers of the gradients)
+  void AllReduceAverageAsync(float* buf, size_t offset, size_t count, cudaStream_t comm);
   int reserved_sms() const { return nccl_ctas_; }               // SMs the collective's CTAs need while it is in flight
  private:
   void* comm_ = nullptr;
@@ -149,8 +149,12 @@ class ConvNet {
   void WaitSide();
   DataParallelSync* dp_ = nullptr;
   std::vector<Bucket> buckets_;
-  cudaStream_t side_ = nullptr;
-  cudaEvent_t ev_main_ = nullptr, ev_side_ = nullptr;
+  // side_: bias-gradient passes and the per-bucket SGD steps; comm_: the NCCL all-reduces only, so that a long exchange
+  // (fc6: 302 MB) never delays the column sums or the optimizer steps of other buckets queued behind it
+  cudaStream_t side_ = nullptr, comm_ = nullptr;
+  cudaEvent_t ev_main_ = nullptr, ev_side_ = nullptr, ev_comm_ = nullptr;
+  std::vector<cudaEvent_t> ev_reduced_;         // per bucket: its all-reduce has finished (comm_ -> side_ / main)
+  bool comm_pending_ = false;
   SideLane lane_;                               // what the edges see of the side stream (bias-gradient passes)
   bool eager_update_ = false, side_pending_ = false, updated_in_bprop_ = false;
   bool dropout_active_ = false;                 // the last Fprop applied dropout (train == true): states hold relu(x) * mask

@@ -75,7 +75,9 @@ void EdgeWithWeight::SetHistoryMemory(Matrix& p) {
 void EdgeWithWeight::StageForUp(Matrix& input) {
   if (convnet_b200_get_conv_precision() != 2) return;
   if (bf_up_ == 1 || bf_outer_ == 1) convnet_b200_bf16_ensure(input.GetDevData(), (long long)input.GetNumEls());
-  if (bf_up_ == 1 || bf_down_ == 1) convnet_b200_bf16_ensure(weights_.GetDevData(), (long long)weights_.GetNumEls());
+  // the weights: also on the very first step (paths still unknown) — FC-shaped calls take the bf16 path only when they find
+  // the copy, and from then on the SGD kernel keeps it fresh; an edge that turns out to stay on tf32 drops it again
+  if (bf_up_ != 0 || bf_down_ != 0) convnet_b200_bf16_ensure(weights_.GetDevData(), (long long)weights_.GetNumEls());
 }
 void EdgeWithWeight::StageForBprop(Matrix& deriv_output) {
   if (convnet_b200_get_conv_precision() != 2) return;
@@ -92,7 +94,10 @@ void EdgeWithWeight::SumBiasRows(Matrix& deriv_output, float scale_targets, floa
   side_->used = true;
 }
 void EdgeWithWeight::NoteUp() { bf_up_ = convnet_b200_last_conv_path() == 2 ? 1 : 0; }
-void EdgeWithWeight::NoteDown() { bf_down_ = convnet_b200_last_conv_path() == 2 ? 1 : 0; }
+void EdgeWithWeight::NoteDown() {
+  bf_down_ = convnet_b200_last_conv_path() == 2 ? 1 : 0;
+  if (bf_up_ == 0 && bf_down_ == 0) convnet_b200_bf16_invalidate(weights_.GetDevData());     // nobody reads the bf16 weights
+}
 void EdgeWithWeight::NoteOuter() { bf_outer_ = convnet_b200_last_conv_path() == 2 ? 1 : 0; }
 
 void EdgeWithWeight::AppendSgdTensors(std::vector<CnbSgdTensor>& out) {   // src/optimizer.cc:174-200 (SGD + momentum + L2)
