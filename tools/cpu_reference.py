@@ -40,6 +40,7 @@ def _backend():
 # Bounded samples, smallest first.  A full step is ~30 s per image on an idle core but minutes when 128 worker processes
 # share the memory system, so the sample is chosen per box from a calibration run to fit a time budget.
 SAMPLES = (("nin2_1",), ("conv3", "nin3_1", "fc7"), None)      # None = all 14 weighted edges
+NOMINAL_S_PER_GFLOP = 2.3        # seconds per GFLOP on one core while all cores run the reference's naive sgemm (128-core box)
 
 
 def flops_per_image(layers=None):
@@ -99,7 +100,6 @@ class Pool:
         self.cores = cores or os.cpu_count() or 1
         self.pool = mp.get_context("spawn").Pool(self.cores)
         _, self.kind = _backend()
-        self.sec_per_gflop = None            # slowest core, all cores busy; set by the calibration run
 
     def close(self):
         self.pool.close(); self.pool.join()
@@ -111,23 +111,21 @@ class Pool:
 
     def step(self, budget_s=25.0, images_per_core=1):
         """one bounded sample: every core pushes images_per_core image(s) through the largest layer set of SAMPLES whose
-        predicted time fits budget_s (prediction from a calibration run of the smallest set on this box, all cores busy);
-        images/s of the whole step is extrapolated by FLOPs when the set is not the full one.
-        Returns (images_per_second, description)."""
-        if self.sec_per_gflop is None:
-            slow, _ = self._run(SAMPLES[0])
-            self.sec_per_gflop = slow / (flops_per_image(SAMPLES[0]) / 1e9)
+        NOMINAL time fits budget_s.  The choice depends on the budget only (i.e. on the command line), never on how busy
+        the box happens to be: the nominal cost is NOMINAL_S_PER_GFLOP seconds per GFLOP per core with every core busy
+        (measured on the 128-core bench boxes in round 1; an 8-core box is ~3x faster per core).  images/s of the whole
+        step is extrapolated by FLOPs when the set is not the full one.  Returns (images_per_second, description)."""
         layers = SAMPLES[0]
         for cand in SAMPLES[1:]:
-            if self.sec_per_gflop * flops_per_image(cand) / 1e9 * images_per_core <= budget_s:
+            if NOMINAL_S_PER_GFLOP * flops_per_image(cand) / 1e9 * images_per_core <= budget_s:
                 layers = cand
         slow, wall = self._run(layers, images_per_core)
         images = images_per_core * self.cores
         frac = flops_per_image(layers) / flops_per_image(None)
         value = images * frac / slow           # every core finishes its share within `slow` seconds
         what = "all 14 weighted edges" if layers is None else \
-            "layers %s (%.1f%% of the step's FLOPs, images/s extrapolated by FLOPs; chosen to fit %.0f s on this box)" % (
-                "+".join(layers), 100 * frac, budget_s)
+            "layers %s (%.1f%% of the step's FLOPs, images/s extrapolated by FLOPs; the set is fixed by the per-step budget of " \
+            "%.0f s at a nominal %.1f s/GFLOP/core, not by box load)" % ("+".join(layers), 100 * frac, budget_s, NOMINAL_S_PER_GFLOP)
         desc = ("AlexNet (CLS_net_20140801232522) training step on the host CPU: conv/1x1/fc fprop+dgrad+wgrad of %s, "
                 "%.2f GFLOP/image, %d image(s)/core x %d cores; pool/rnorm/elementwise (<0.1%% of CPU time) omitted; "
                 "slowest core %.1f s inside the reference's conv calls, wall %.1f s" % (
