@@ -128,7 +128,7 @@ void do_pool(const char* what, bool is_max, cudamat* images, cudamat* targets, S
   PoolGeom g = pool_geom(*is, *ts, images, targets, d, what);
   const Fuse fuse = take_fuse();
   Emit emit(targets->data_device, (long long)targets->size[0] * targets->size[1], fuse.emit_bf16 != 0);
-  emit.done = pool_forward(g, is_max, images->data_device, targets->data_device, so, emit.buf);
+  emit.done = pool_forward(g, is_max, images->data_device, targets->data_device, so, emit.buf, fuse.pool_cache != 0);
   emit.finish();
 }
 void do_max_undo(const char* what, cudamat* images, cudamat* maxGrads, cudamat* maxActs, cudamat* targets,

@@ -55,6 +55,7 @@ struct Fuse {
   const float* bias = nullptr;       // fprop: + bias[output channel]
   int relu = 0;                      // fprop: max(., 0) after the bias
   const float* relu_mask = nullptr;  // dgrad / pool undo: result zeroed where relu_mask <= 0 (same shape as the target)
+  int pool_cache = 0;                // MaxPool*: also record the tie masks for the matching MaxPoolUndo* (convnet_b200_pool_cache_next)
   float out_scale = 1.f;             // dgrad: result multiplied by this (the kept-unit scale of a dropout layer, see ext.h)
   int emit_bf16 = 0;                 // any writer: also leave a staged bf16 copy of the whole target (convnet_b200_emit_bf16_next)
   // the writer also produces the bias gradient of the edge that consumes the target as its output derivative

@@ -50,6 +50,9 @@ struct DgradPhase {
 struct DgradBanks { int count; DgradPhase phase[kMaxDgradPhases]; };
 int dgrad_phases(const ConvGeom& g, DgradBanks* b);                    // number of phases, or -1 if there are too many
 const __nv_bfloat16* dgrad_weights(const float* filters, const ConvGeom& g, const DgradBanks& b);   // built on first use, cached
+// max-pool tie masks (stage.cu), see pool.cu
+uint16_t* pool_masks_slot(const float* acts, long long n_out, const float* images, long long n_in, unsigned long long sig);
+const uint16_t* pool_masks_find(const float* acts, long long n_out, const float* images, unsigned long long sig);
 // writer protocol: begin_write drops stale copies and returns the buffer the kernel must fill when it can emit; end_write
 // falls back to a conversion pass when emission was wanted but the kernel could not do it
 __nv_bfloat16* begin_write(float* target, long long n, bool want_emit, bool kernel_can_emit);
@@ -58,7 +61,7 @@ void end_write(float* target, long long n, bool want_emit, const __nv_bfloat16* 
 // pool.cu
 // targets_bf16 (may be null): also write the bf16 twin of the target; the return value says whether the kernel did
 bool pool_forward(const PoolGeom& g, bool is_max, const float* images, float* targets, float scaleOutput,
-                  __nv_bfloat16* targets_bf16 = nullptr);
+                  __nv_bfloat16* targets_bf16 = nullptr, bool cache_masks = false);
 // colsum / colsum_slices (may be null): where a kernel that can do so leaves per-slice channel sums of the tensor it wrote,
 // colsum[slice * channels + c] (*colsum_slices = number of slices, 0 = not done) — the bias gradient of the edge below
 bool max_pool_undo(const PoolGeom& g, const float* images, const float* maxGrads, const float* maxActs,

@@ -83,6 +83,7 @@ void convnet_b200_fuse_next_bias_grad(float* grad_bias, float scaleTargets, floa
   state().fuse.bias_grad = grad_bias; state().fuse.bg_st = scaleTargets; state().fuse.bg_so = scaleOutput;
 }
 void convnet_b200_fuse_next_scale(float scale) { state().fuse.out_scale = scale; }
+void convnet_b200_pool_cache_next(void) { state().fuse.pool_cache = 1; }
 void convnet_b200_reserve_sms(int n) { state().sm_reserve = n > 0 ? n : 0; }
 void convnet_b200_bf16_stage(const float* ptr, long long n) { bf16_stage(ptr, n); }
 void convnet_b200_bf16_ensure(const float* ptr, long long n) { bf16_ensure(ptr, n); }

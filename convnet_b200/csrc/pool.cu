@@ -213,13 +213,15 @@ __device__ __forceinline__ void cover_s(int X, int s, int p, int k, int mods, in
 template <int VEC, bool MAX, int K, int S>
 __global__ void __launch_bounds__(256) pool_fwd_rows_kernel(PoolGeom g, const float* __restrict__ images,
                                                              float* __restrict__ targets, float so, int nv_shift,
-                                                             __nv_bfloat16* __restrict__ targets16) {
+                                                             __nv_bfloat16* __restrict__ targets16,
+                                                             uint16_t* __restrict__ tie_masks) {
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * g.modX;
   const int sx = S > 0 ? S : g.sx, sy = S > 0 ? S : g.sy;
   const float* img = images + (long long)g.N * g.W * g.H * blockIdx.y;        // this channel's input plane
   float* out = targets + (long long)g.N * g.modX * g.modY * blockIdx.y;
   __nv_bfloat16* out16 = targets16 ? targets16 + (long long)g.N * g.modX * g.modY * blockIdx.y : nullptr;
+  uint16_t* outm = (MAX && tie_masks) ? tie_masks + (long long)g.N * g.modX * g.modY * blockIdx.y : nullptr;
   for (int my = blockIdx.x; my < g.modY; my += gridDim.x) {
     const int Y0 = my * sy + g.py;
     for (unsigned t = threadIdx.x; t < rowlen; t += blockDim.x) {
@@ -250,6 +252,20 @@ __global__ void __launch_bounds__(256) pool_fwd_rows_kernel(PoolGeom g, const fl
       if (!MAX) {
 #pragma unroll
         for (int v = 0; v < VEC; v++) acc[v] = acc[v] / region;             // CLIPPED count: gemm.cu:185
+      }
+      if (MAX && outm) {          // bit q = dx + K*dy: that window element equals the maximum; bit 15: the maximum is > 0
+        uint16_t mk[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; v++) mk[v] = acc[v] > 0.f ? 0x8000 : 0;
+#pragma unroll
+        for (int q = 0; q < K * K; q++)
+          if (ok[q]) {
+#pragma unroll
+            for (int v = 0; v < VEC; v++) mk[v] |= (a[q][v] == acc[v]) ? (uint16_t)(1u << q) : (uint16_t)0;
+          }
+        uint16_t* dstm = outm + (unsigned)(my * rowlen + t) * VEC;
+        if (VEC == 4) *reinterpret_cast<uint2*>(dstm) = make_uint2((uint32_t)mk[0] | ((uint32_t)mk[1 % VEC] << 16), (uint32_t)mk[2 % VEC] | ((uint32_t)mk[3 % VEC] << 16));
+        else dstm[0] = mk[0];
       }
 #pragma unroll
       for (int v = 0; v < VEC; v++) acc[v] = so * acc[v];
@@ -354,12 +370,106 @@ __global__ void __launch_bounds__(256) pool_undo_rows_kernel(PoolGeom g, const f
   }
 }
 
+// max-pool undo from the tie masks the forward kernel recorded (convnet_b200_pool_cache_next): for an input element,
+// every covering window contributes its gradient iff the mask says this element equalled the window's maximum — the same
+// sum as pool_undo_rows_kernel<MAX>, without loading the pool input or output.  POSITIVE_ONLY: the fused ReLU' mask is the
+// pool input itself and that input is a ReLU output (>= 0): an element passes the mask iff its value — the window maximum
+// it equals — is > 0, which is bit 15.
+template <int VEC, int Q, int S, int K>
+__global__ void __launch_bounds__(256) pool_undo_masked_kernel(PoolGeom g, const float* __restrict__ grads,
+                                                               const uint16_t* __restrict__ tie_masks, float* targets,
+                                                               float st, float so, int positive_only, int nv_shift,
+                                                               __nv_bfloat16* __restrict__ targets16, float* __restrict__ rowsum) {
+  const unsigned NV = g.N / VEC;
+  const unsigned rowlen = NV * g.W;
+  const long long in_plane = (long long)g.N * g.W * g.H * blockIdx.y, out_plane = (long long)g.N * g.modX * g.modY * blockIdx.y;
+  const float* gr_p = grads + out_plane;
+  const uint16_t* mk_p = tie_masks + out_plane;
+  float* out = targets + in_plane;
+  __nv_bfloat16* out16 = targets16 ? targets16 + in_plane : nullptr;
+  const int sx = S > 0 ? S : g.sx, sy = S > 0 ? S : g.sy;
+  float total = 0.f;
+  for (int Y = blockIdx.x; Y < g.H; Y += gridDim.x) {
+    int y0, y1;
+    cover_s<S>(Y, g.sy, g.py, g.ky, g.modY, y0, y1);
+    for (unsigned t = threadIdx.x; t < rowlen; t += blockDim.x) {
+      const unsigned X = nv_shift >= 0 ? (t >> nv_shift) : t / NV;
+      const unsigned nv = t - X * NV;
+      const unsigned idx = (unsigned)(Y * rowlen + t) * VEC;
+      int x0, x1;
+      cover_s<S>((int)X, g.sx, g.px, g.kx, g.modX, x0, x1);
+      float acc[VEC], old[VEC];
+#pragma unroll
+      for (int v = 0; v < VEC; v++) { acc[v] = 0.f; old[v] = 0.f; }
+      if (st != 0.f) vload<VEC>(out + idx, old);
+      float gr[Q * Q][VEC];
+      uint16_t mk[Q * Q][VEC];
+      bool ok[Q * Q];
+#pragma unroll
+      for (int j = 0; j < Q; j++)
+#pragma unroll
+        for (int i = 0; i < Q; i++) {
+          const int mx = x0 + i, my = y0 + j;
+          ok[j * Q + i] = mx <= x1 && my <= y1;
+          if (ok[j * Q + i]) {
+            const unsigned off = (unsigned)((my * g.modX + mx) * g.N) + nv * VEC;
+            vload<VEC>(gr_p + off, gr[j * Q + i]);
+            if (VEC == 4) {
+              const uint2 m = __ldg(reinterpret_cast<const uint2*>(mk_p + off));
+              mk[j * Q + i][0] = (uint16_t)(m.x & 0xFFFF); mk[j * Q + i][1 % VEC] = (uint16_t)(m.x >> 16);
+              mk[j * Q + i][2 % VEC] = (uint16_t)(m.y & 0xFFFF); mk[j * Q + i][3 % VEC] = (uint16_t)(m.y >> 16);
+            } else mk[j * Q + i][0] = __ldg(mk_p + off);
+          }
+        }
+#pragma unroll
+      for (int j = 0; j < Q; j++)
+#pragma unroll
+        for (int i = 0; i < Q; i++)
+          if (ok[j * Q + i]) {
+            const int bit = ((int)X - ((x0 + i) * sx + g.px)) + K * (Y - ((y0 + j) * sy + g.py));     // element's place in that window
+            const uint16_t need = (uint16_t)((1u << bit) | (positive_only ? 0x8000u : 0u));
+#pragma unroll
+            for (int v = 0; v < VEC; v++) acc[v] += ((mk[j * Q + i][v] & need) == need) ? so * gr[j * Q + i][v] : 0.f;
+          }
+#pragma unroll
+      for (int v = 0; v < VEC; v++) acc[v] += st * old[v];
+      vstore<VEC>(out + idx, acc);
+      if (out16) vemit<VEC>(out16 + idx, acc);
+      if (rowsum) {
+#pragma unroll
+        for (int v = 0; v < VEC; v++) total += acc[v];
+      }
+    }
+  }
+  if (rowsum) {
+    __shared__ float sh[8];
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < 8; w++) s += sh[w];
+      rowsum[(size_t)blockIdx.x * gridDim.y + blockIdx.y] = s;
+    }
+  }
+}
+
 static int pow2_shift(unsigned v) { int s = 0; while ((1u << s) < v) s++; return (1u << s) == v ? s : -1; }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+static unsigned long long pool_sig(const PoolGeom& g) {
+  unsigned long long sig = 1469598103934665603ULL;
+  for (int v : {g.N, g.W, g.H, g.C, g.modX, g.modY, g.kx, g.ky, g.sx, g.sy, g.px, g.py}) sig = (sig ^ (unsigned)v) * 1099511628211ULL;
+  return sig;
+}
+static bool masks_supported(const PoolGeom& g) {      // the row kernels, windows up to 3 x 3 (9 tie bits + the sign bit)
+  return g.kt == 1 && g.T == 1 && g.modT == 1 && std::max(g.kx, g.ky) <= 3 && g.sx == g.sy && (long long)g.N * g.W * g.H < (1LL << 31);
+}
+
 template <int VEC, bool MAX>
-static bool launch_fwd(const PoolGeom& g, const float* images, float* targets, float so, long long total, __nv_bfloat16* t16) {
+static bool launch_fwd(const PoolGeom& g, const float* images, float* targets, float so, long long total, __nv_bfloat16* t16,
+                       uint16_t* masks) {
   cudaStream_t s = state().stream;
   const int planes = g.C * g.modT;
   const long long per_plane = total / planes;
@@ -371,7 +481,7 @@ static bool launch_fwd(const PoolGeom& g, const float* images, float* targets, f
     const dim3 rgrid((unsigned)g.modY, planes);
     const int sh = pow2_shift(g.N / VEC);
     const int S = (g.sx == g.sy && g.sx <= 2) ? g.sx : 0;
-#define CNB_POOL_FWD(KK, SS) pool_fwd_rows_kernel<VEC, MAX, KK, SS><<<rgrid, 256, 0, s>>>(g, images, targets, so, sh, t16)
+#define CNB_POOL_FWD(KK, SS) pool_fwd_rows_kernel<VEC, MAX, KK, SS><<<rgrid, 256, 0, s>>>(g, images, targets, so, sh, t16, masks)
     if (k <= 2) { if (S == 1) CNB_POOL_FWD(2, 1); else if (S == 2) CNB_POOL_FWD(2, 2); else CNB_POOL_FWD(2, 0); }
     else { if (S == 1) CNB_POOL_FWD(3, 1); else if (S == 2) CNB_POOL_FWD(3, 2); else CNB_POOL_FWD(3, 0); }
 #undef CNB_POOL_FWD
@@ -384,16 +494,21 @@ static bool launch_fwd(const PoolGeom& g, const float* images, float* targets, f
   return false;
 }
 
-bool pool_forward(const PoolGeom& g, bool is_max, const float* images, float* targets, float so, __nv_bfloat16* targets_bf16) {
+bool pool_forward(const PoolGeom& g, bool is_max, const float* images, float* targets, float so, __nv_bfloat16* targets_bf16,
+                  bool cache_masks) {
   const bool v4 = (g.N % 4 == 0) && aligned16(images) && aligned16(targets);
   const long long outs = (long long)g.modX * g.modY * g.C * g.modT;
+  // tie masks for the matching undo: only from the row kernels with K == 3 bit layout (k <= 3), unscaled outputs
+  uint16_t* masks = nullptr;
+  if (cache_masks && is_max && so == 1.f && masks_supported(g) && std::max(g.kx, g.ky) == 3)
+    masks = pool_masks_slot(targets, outs * g.N, images, (long long)g.N * g.W * g.H * g.C, pool_sig(g));
   bool emitted;
   if (v4) {
-    if (is_max) emitted = launch_fwd<4, true>(g, images, targets, so, outs * (g.N / 4), targets_bf16);
-    else emitted = launch_fwd<4, false>(g, images, targets, so, outs * (g.N / 4), targets_bf16);
+    if (is_max) emitted = launch_fwd<4, true>(g, images, targets, so, outs * (g.N / 4), targets_bf16, masks);
+    else emitted = launch_fwd<4, false>(g, images, targets, so, outs * (g.N / 4), targets_bf16, nullptr);
   } else {
-    if (is_max) emitted = launch_fwd<1, true>(g, images, targets, so, outs * g.N, targets_bf16);
-    else emitted = launch_fwd<1, false>(g, images, targets, so, outs * g.N, targets_bf16);
+    if (is_max) emitted = launch_fwd<1, true>(g, images, targets, so, outs * g.N, targets_bf16, masks);
+    else emitted = launch_fwd<1, false>(g, images, targets, so, outs * g.N, targets_bf16, nullptr);
   }
   count_launch();
   CNB_LAUNCH_CHECK("pool_forward");
@@ -416,6 +531,19 @@ static bool launch_undo(const PoolGeom& g, const float* images, const float* gra
     const dim3 rgrid((unsigned)g.H, planes);
     const int sh = pow2_shift(g.N / VEC);
     const int S = (g.sx == g.sy && g.sx <= 2) ? g.sx : 0;
+    // the forward pass left tie masks for exactly this (input, output) pair and nothing wrote either since: no need to
+    // reload and compare them.  A fused ReLU' mask is only expressible when it IS the pool input (bit 15 = maximum > 0).
+    if (MAX && q == 2 && std::max(g.kx, g.ky) == 3 && masks_supported(g) && (mask == nullptr || mask == images)) {
+      const uint16_t* tm = pool_masks_find(acts, (long long)g.N * g.modX * g.modY * g.C, images, pool_sig(g));
+      if (tm) {
+        if (colsum && colsum_slices) *colsum_slices = g.H;
+        const int pos = mask != nullptr ? 1 : 0;
+        if (S == 2) pool_undo_masked_kernel<VEC, 2, 2, 3><<<rgrid, 256, 0, s>>>(g, grads, tm, targets, st, so, pos, sh, t16, colsum);
+        else if (S == 1) pool_undo_masked_kernel<VEC, 2, 1, 3><<<rgrid, 256, 0, s>>>(g, grads, tm, targets, st, so, pos, sh, t16, colsum);
+        else pool_undo_masked_kernel<VEC, 2, 0, 3><<<rgrid, 256, 0, s>>>(g, grads, tm, targets, st, so, pos, sh, t16, colsum);
+        return t16 != nullptr;
+      }
+    }
     if (colsum && colsum_slices) *colsum_slices = g.H;
 #define CNB_POOL_UNDO(QQ, SS) pool_undo_rows_kernel<VEC, MAX, QQ, SS><<<rgrid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, mask, sh, t16, colsum)
     if (q <= 1) { if (S == 1) CNB_POOL_UNDO(1, 1); else if (S == 2) CNB_POOL_UNDO(1, 2); else CNB_POOL_UNDO(1, 0); }

@@ -21,8 +21,9 @@ namespace {
 
 struct Staged {
   const float* src; long long n; __nv_bfloat16* buf; size_t cap; bool valid; unsigned long long tick; int dev;
-  int kind;                         // 0: plain bf16 copy; 1: dgrad weight banks (dgrad_weights), `sig` = geometry they were built for
-  unsigned long long sig;
+  int kind;                         // 0: plain bf16 copy; 1: dgrad weight banks (dgrad_weights), `sig` = geometry they were built for;
+  unsigned long long sig;           // 2: max-pool tie masks of the pooled tensor `src` (pool_masks_*), `src2` = the pool input
+  const float* src2; long long n2;  // kind 2: a write to EITHER tensor makes the masks stale
 };
 std::vector<Staged>& table() { static std::vector<Staged> t; return t; }
 unsigned long long g_tick = 0;
@@ -93,7 +94,7 @@ Staged* acquire_slot(const float* ptr, long long n, int kind = 0) {
       slot = &t[0];
       for (Staged& e : t) if (e.tick < slot->tick) slot = &e;
     } else {
-      t.push_back(Staged{ptr, 0, nullptr, 0, false, 0, dev, kind, 0});
+      t.push_back(Staged{ptr, 0, nullptr, 0, false, 0, dev, kind, 0, nullptr, 0});
       slot = &t.back();
     }
   }
@@ -110,6 +111,7 @@ Staged* acquire_slot(const float* ptr, long long n, int kind = 0) {
     slot->cap = bytes;
   }
   slot->src = ptr; slot->n = n; slot->dev = dev; slot->valid = false; slot->tick = ++g_tick; slot->kind = kind; slot->sig = 0;
+  slot->src2 = nullptr; slot->n2 = 0;
   return slot;
 }
 
@@ -220,8 +222,11 @@ void bf16_invalidate(const float* ptr) {
 void bf16_note_write(const float* ptr, long long n) {
   if (table().empty() || ptr == nullptr) return;
   const int dev = current_device();
-  for (Staged& e : table())
-    if (e.valid && e.dev == dev && ptr < e.src + e.n && e.src < ptr + n) e.valid = false;
+  for (Staged& e : table()) {
+    if (!e.valid || e.dev != dev) continue;
+    if (ptr < e.src + e.n && e.src < ptr + n) e.valid = false;
+    else if (e.src2 && ptr < e.src2 + e.n2 && e.src2 < ptr + n) e.valid = false;
+  }
 }
 
 void bf16_release() {
@@ -263,6 +268,22 @@ __nv_bfloat16* bf16_refresh_slot(const float* ptr, long long n) {
   if (!e || e->n != n || !e->buf) return nullptr;
   e->valid = true; e->tick = ++g_tick;
   return e->buf;
+}
+
+// max-pool tie masks: one uint16 per pooled element (bit dx + K*dy set where the window element equals the max, bit 15 where
+// the max is > 0), written by the forward kernel on request and read by the undo kernel instead of the pool input and output
+uint16_t* pool_masks_slot(const float* acts, long long n_out, const float* images, long long n_in, unsigned long long sig) {
+  if (acts == nullptr || n_out <= 0) return nullptr;
+  Staged* e = acquire_slot(acts, n_out, 2);          // n_out uint16 == n_out bf16-sized elements
+  e->src2 = images; e->n2 = n_in; e->sig = sig; e->valid = true;
+  return reinterpret_cast<uint16_t*>(e->buf);
+}
+const uint16_t* pool_masks_find(const float* acts, long long n_out, const float* images, unsigned long long sig) {
+  if (table().empty()) return nullptr;
+  Staged* e = find_slot(acts, current_device(), 2);
+  if (!e || !e->valid || e->n != n_out || e->src2 != images || e->sig != sig) return nullptr;
+  e->tick = ++g_tick;
+  return reinterpret_cast<const uint16_t*>(e->buf);
 }
 
 __nv_bfloat16* begin_write(float* target, long long n, bool want_emit, bool kernel_can_emit) {

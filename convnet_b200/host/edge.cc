@@ -432,6 +432,10 @@ void MaxPoolEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool 
     exit(1);
   }
   if (emit_up_) convnet_b200_emit_bf16_next();
+  // training: have the kernel record which window elements equal the maximum; ComputeDown then reads those masks instead of
+  // re-reading and comparing input and output (nothing between the two calls writes either tensor except through the library,
+  // which drops the masks when it does)
+  if (train) convnet_b200_pool_cache_next();
   Matrix::ConvMaxPool(input, output, conv_desc_);
 }
 void MaxPoolEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) {

@@ -55,6 +55,15 @@ void convnet_b200_fuse_next_bias_grad(float* grad_bias, float scaleTargets, floa
  * ApplyDerivativeOfActivation, src/layer.cc:367-395,562-580)  ==  deriv * 1/(1-p) * [state > 0]. */
 void convnet_b200_fuse_next_scale(float scale);
 
+/* One-shot: the NEXT MaxPool* call also records which elements of every window equal its maximum (one 16-bit mask per
+ * pooled element, in library scratch).  The MaxPoolUndo* call on the same (images, maxActs) pair then reads the gradients
+ * and those masks instead of re-reading the pool input and output and comparing — 0.55x the bytes of the largest
+ * memory-bound pass of the step, bit-identical results (ties duplicate the gradient exactly as kMaxPoolUndo's `==` test
+ * does, cudamat_conv_gemm.cu:262-300).  The masks go stale, and the undo falls back to comparing, as soon as any entry
+ * point of this library writes either tensor; a caller that overwrites them by other means between the two calls must
+ * not use this request (or must call convnet_b200_bf16_invalidate(NULL)).  2-D windows up to 3 x 3. */
+void convnet_b200_pool_cache_next(void);
+
 /* The conv kernels are persistent: one CTA (or CTA pair) per SM, each owning most of the SM's shared memory.  A kernel
  * of another library that must run CONCURRENTLY (an NCCL collective on a side stream) cannot co-reside with them and
  * would otherwise wait for — or push out — a whole wave.  convnet_b200_reserve_sms(n) makes the persistent grids leave

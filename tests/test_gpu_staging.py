@@ -73,3 +73,55 @@ def test_library_writes_keep_copies_coherent():
     finally:
         L.convnet_b200_bf16_invalidate(None)
         lib.set_precision("fp32")
+
+
+@pytest.mark.parametrize("shape", [(128, 27, 27, 64), (32, 110, 110, 8), (7, 9, 9, 5)])
+def test_max_pool_undo_from_tie_masks_is_bit_identical(shape):
+    """convnet_b200_pool_cache_next: the undo fed by the forward pass's tie masks equals the compare-based undo bit for bit —
+    with ties (quantised inputs), with scaleTargets, with the fused ReLU' mask that is the pool input, and it falls back as
+    soon as the library writes one of the two tensors."""
+    import torch
+    from convnet_b200 import conv_gemm as cg
+    from convnet_b200 import lib
+    from convnet_b200.abi import GetConvDesc, num_modules
+    from convnet_b200.matrix import CUDAMatrix
+    L = lib.load()
+    N, W, H, C = shape
+    mod = num_modules(W, 3, 2, 1)
+    d = GetConvDesc(C, C, 3, 3, 2, 2, 1, 1)
+    ish, psh = (N, W, H, C), (N, mod, mod, C)
+    g = torch.Generator(device="cuda").manual_seed(4)
+    x = CUDAMatrix(N, W * H * C, ish)
+    x.storage.copy_(torch.round(torch.randn(x.storage.numel(), device="cuda", generator=g) * 2) / 2)      # many ties, both signs
+    gr = CUDAMatrix(N, mod * mod * C, psh); gr.storage.normal_(generator=g)
+    init = torch.randn(x.storage.numel(), device="cuda", generator=g)
+    try:
+        for with_mask in (False, True):
+            for st in (0.0, 1.0):
+                # compare-based reference path
+                acts = CUDAMatrix(N, mod * mod * C, psh); cg.MaxPool(x, acts, d)
+                ref = CUDAMatrix(N, W * H * C, ish); ref.storage.copy_(init)
+                if with_mask:
+                    L.convnet_b200_fuse_next(None, 0, x.ptr)
+                cg.MaxPoolUndo(x, gr, acts, ref, d, st)
+                # mask-based path
+                acts2 = CUDAMatrix(N, mod * mod * C, psh)
+                L.convnet_b200_pool_cache_next(); cg.MaxPool(x, acts2, d)
+                assert torch.equal(acts.storage, acts2.storage)
+                out = CUDAMatrix(N, W * H * C, ish); out.storage.copy_(init)
+                if with_mask:
+                    L.convnet_b200_fuse_next(None, 0, x.ptr)
+                cg.MaxPoolUndo(x, gr, acts2, out, d, st)
+                assert torch.equal(out.storage, ref.storage), (with_mask, st)
+        # a library write to the pool input drops the masks: the undo must follow the CURRENT tensors (compare path)
+        acts2 = CUDAMatrix(N, mod * mod * C, psh)
+        L.convnet_b200_pool_cache_next(); cg.MaxPool(x, acts2, d)
+        L.cnb_relu(x.ptr, x.storage.numel())
+        ref = CUDAMatrix(N, W * H * C, ish); out = CUDAMatrix(N, W * H * C, ish)
+        cg.MaxPoolUndo(x, gr, acts2, out, d, 0)
+        x2 = CUDAMatrix(N, W * H * C, ish); x2.storage.copy_(x.storage)
+        acts3 = CUDAMatrix(N, mod * mod * C, psh); acts3.storage.copy_(acts2.storage)
+        cg.MaxPoolUndo(x2, gr, acts3, ref, d, 0)
+        assert torch.equal(out.storage, ref.storage)
+    finally:
+        L.convnet_b200_bf16_invalidate(None)
