@@ -168,11 +168,11 @@ def conv_roofline(torch, lib, peaks, peak_kind, iters=10):
     traffic = None                          # DRAM bytes per launch from the committed ncu --set full capture of this kernel
     if path == "tcgen05-bf16":
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r1_conv4_fprop_bf16_ncu.json")))["traffic_bytes_per_launch"]
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r2_conv4_fprop_fast_ncu.json")))["traffic_bytes_per_launch"]
         except Exception:
             traffic = None
     return {"bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
-            "traffic": traffic, "kernel": "tc_conv_kernel<fprop> (%s)" % path,
+            "traffic": traffic, "kernel": "tc_fast_kernel<fprop, pair> (%s)" % path,
             "shape": "conv4 fprop 3x3 s1 p1, 14x14x768 -> 384, batch 256 (266.3 GFLOP)", "ms_per_launch": ms,
             "back_to_back": None if not ms_warm else {"ms": ms_warm, "tflops": flops / (ms_warm * 1e-3) / 1e12,
                                                      "note": "same staged launch without the L2 flush between launches"},
@@ -313,6 +313,9 @@ def main():
         replicas_identical = all(int(t.item()) == int(sums[0].item()) for t in sums)
         assert replicas_identical, "parameters diverged across ranks: %s" % [int(t.item()) for t in sums]
 
+    # where the step's time goes on this rank: one traced step after the timed region (not part of any reported rate)
+    timeline = net.trace_step()
+
     # BASELINE config 3 quotes the data-parallel run at 256 images per GPU: a second, shorter measurement of the same step at
     # that per-GPU batch (same net, same NCCL path), reported inside `config` — the headline stays config 2's batch 128
     cfg3 = None
@@ -362,6 +365,7 @@ def main():
             "roofline": roof,
             "last_loss": losses[-1] if losses else None,
             "param_checksum": int(checksum.item()), "replicas_identical": replicas_identical,
+            "timeline_rank0": timeline,
         }
         if world == 1 and not args.no_cpu_baseline:
             import cpu_reference

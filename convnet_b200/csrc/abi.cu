@@ -140,7 +140,7 @@ void do_max_undo(const char* what, cudamat* images, cudamat* maxGrads, cudamat* 
   const Fuse fuse = take_fuse();
   Emit emit(targets->data_device, (long long)targets->size[0] * targets->size[1], fuse.emit_bf16 != 0);
   int slices = 0;
-  float* part = fuse.bias_grad ? (float*)workspace(sizeof(float) * (size_t)g.H * g.C * g.T) : nullptr;
+  float* part = fuse.bias_grad ? (float*)workspace(sizeof(float) * (size_t)(g.H + 2) * g.C * g.T) : nullptr;
   emit.done = max_pool_undo(g, images->data_device, maxGrads->data_device, maxActs->data_device, targets->data_device, st,
                             1.f, fuse.relu_mask, emit.buf, g.T == 1 ? part : nullptr, &slices);
   finish_bias_grad(fuse, part, slices, targets->data_device, (long long)g.N * g.W * g.H * g.T, g.C);
@@ -153,7 +153,7 @@ void do_avg_undo(const char* what, cudamat* avgGrads, cudamat* targets, Shape4D*
   const Fuse fuse = take_fuse();
   Emit emit(targets->data_device, (long long)targets->size[0] * targets->size[1], fuse.emit_bf16 != 0);
   int slices = 0;
-  float* part = fuse.bias_grad ? (float*)workspace(sizeof(float) * (size_t)g.H * g.C * g.T) : nullptr;
+  float* part = fuse.bias_grad ? (float*)workspace(sizeof(float) * (size_t)(g.H + 2) * g.C * g.T) : nullptr;
   emit.done = avg_pool_undo(g, avgGrads->data_device, targets->data_device, st, so, fuse.relu_mask, emit.buf,
                             g.T == 1 ? part : nullptr, &slices);
   finish_bias_grad(fuse, part, slices, targets->data_device, (long long)g.N * g.W * g.H * g.T, g.C);

@@ -454,6 +454,195 @@ __global__ void __launch_bounds__(256) pool_undo_masked_kernel(PoolGeom g, const
   }
 }
 
+// The same undo for stride 2, windows up to 3 x 3, organised by PATCHES: the 2 x 2 input elements whose offset from the
+// padded origin is (2*mx + a, 2*my + b) are covered by the same 2 x 2 windows {mx-1, mx} x {my-1, my}, so one thread loads
+// those four (gradient, mask) pairs once and writes four outputs — a quarter of the L2 requests of the per-element kernel
+// above, which is what bounded it (13 TB/s of L2 reads for 3 TB/s of DRAM traffic on pool1).  Sums run over the windows in
+// the same ascending (y, x) order as the per-element kernels: results are bit-identical to them.
+template <int VEC>
+__global__ void __launch_bounds__(256) pool_undo_masked_patch_kernel(PoolGeom g, const float* __restrict__ grads,
+                                                                     const uint16_t* __restrict__ tie_masks, float* targets,
+                                                                     float st, float so, int positive_only, int nv_shift,
+                                                                     __nv_bfloat16* __restrict__ targets16,
+                                                                     float* __restrict__ rowsum, int PX, int PY) {
+  const unsigned NV = g.N / VEC;
+  const unsigned rowlen = NV * PX;
+  const long long in_plane = (long long)g.N * g.W * g.H * blockIdx.y, out_plane = (long long)g.N * g.modX * g.modY * blockIdx.y;
+  const float* gr_p = grads + out_plane;
+  const uint16_t* mk_p = tie_masks + out_plane;
+  float* out = targets + in_plane;
+  __nv_bfloat16* out16 = targets16 ? targets16 + in_plane : nullptr;
+  const uint16_t sign = positive_only ? (uint16_t)0x8000u : (uint16_t)0;
+  float total = 0.f;
+  for (int my = blockIdx.x; my < PY; my += gridDim.x) {       // patch row my: input rows 2*my + py + {0, 1} (py <= 0)
+    for (unsigned t = threadIdx.x; t < rowlen; t += blockDim.x) {
+      const unsigned mx = nv_shift >= 0 ? (t >> nv_shift) : t / NV;
+      const unsigned nv = t - mx * NV;
+      float gr[4][VEC];
+      uint16_t mk[4][VEC];
+      bool ok[4];
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int wx = (int)mx - 1 + i, wy = my - 1 + j;
+          ok[j * 2 + i] = (unsigned)wx < (unsigned)g.modX && (unsigned)wy < (unsigned)g.modY;
+          if (ok[j * 2 + i]) {
+            const unsigned off = (unsigned)((wy * g.modX + wx) * g.N) + nv * VEC;
+            vload<VEC>(gr_p + off, gr[j * 2 + i]);
+            if (VEC == 4) {
+              const uint2 m = __ldg(reinterpret_cast<const uint2*>(mk_p + off));
+              mk[j * 2 + i][0] = (uint16_t)(m.x & 0xFFFF); mk[j * 2 + i][1 % VEC] = (uint16_t)(m.x >> 16);
+              mk[j * 2 + i][2 % VEC] = (uint16_t)(m.y & 0xFFFF); mk[j * 2 + i][3 % VEC] = (uint16_t)(m.y >> 16);
+            } else mk[j * 2 + i][0] = __ldg(mk_p + off);
+          }
+        }
+#pragma unroll
+      for (int b = 0; b < 2; b++) {
+        const int Y = 2 * my + g.py + b;
+        if ((unsigned)Y >= (unsigned)g.H) continue;
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+          const int X = 2 * (int)mx + g.px + a;
+          if ((unsigned)X >= (unsigned)g.W) continue;
+          const unsigned idx = (unsigned)((Y * g.W + X) * g.N) + nv * VEC;
+          float acc[VEC], old[VEC];
+#pragma unroll
+          for (int v = 0; v < VEC; v++) { acc[v] = 0.f; old[v] = 0.f; }
+          if (st != 0.f) vload<VEC>(out + idx, old);
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            const int dy = 2 * (1 - j) + b;                   // the element's row inside window my-1+j
+            if (dy >= g.ky) continue;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              const int dx = 2 * (1 - i) + a;
+              if (dx >= g.kx || !ok[j * 2 + i]) continue;
+              const uint16_t need = (uint16_t)((1u << (dx + 3 * dy)) | sign);
+#pragma unroll
+              for (int v = 0; v < VEC; v++) acc[v] += ((mk[j * 2 + i][v] & need) == need) ? so * gr[j * 2 + i][v] : 0.f;
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; v++) acc[v] += st * old[v];
+          vstore<VEC>(out + idx, acc);
+          if (out16) vemit<VEC>(out16 + idx, acc);
+          if (rowsum) {
+#pragma unroll
+            for (int v = 0; v < VEC; v++) total += acc[v];
+          }
+        }
+      }
+    }
+  }
+  if (rowsum) {
+    __shared__ float sh[8];
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < 8; w++) s += sh[w];
+      rowsum[(size_t)blockIdx.x * gridDim.y + blockIdx.y] = s;
+    }
+  }
+}
+
+// Compare-based max-pool undo (no cached masks) in the same patch organisation: per thread the 2 x 2 inputs of a patch and
+// the 2 x 2 windows that cover them, each loaded once.
+template <int VEC>
+__global__ void __launch_bounds__(256) pool_undo_patch_kernel(PoolGeom g, const float* __restrict__ images,
+                                                              const float* __restrict__ grads, const float* __restrict__ acts,
+                                                              float* targets, float st, float so,
+                                                              const float* __restrict__ relu_mask, int nv_shift,
+                                                              __nv_bfloat16* __restrict__ targets16,
+                                                              float* __restrict__ rowsum, int PX, int PY) {
+  const unsigned NV = g.N / VEC;
+  const unsigned rowlen = NV * PX;
+  const long long in_plane = (long long)g.N * g.W * g.H * blockIdx.y, out_plane = (long long)g.N * g.modX * g.modY * blockIdx.y;
+  const float* img = images + in_plane;
+  const float* gr_p = grads + out_plane;
+  const float* ac_p = acts + out_plane;
+  const float* mk_p = relu_mask ? relu_mask + in_plane : nullptr;
+  const bool mask_is_input = relu_mask == images;
+  float* out = targets + in_plane;
+  __nv_bfloat16* out16 = targets16 ? targets16 + in_plane : nullptr;
+  float total = 0.f;
+  for (int my = blockIdx.x; my < PY; my += gridDim.x) {
+    for (unsigned t = threadIdx.x; t < rowlen; t += blockDim.x) {
+      const unsigned mx = nv_shift >= 0 ? (t >> nv_shift) : t / NV;
+      const unsigned nv = t - mx * NV;
+      float gr[4][VEC], ac[4][VEC], im[4][VEC];
+      bool ok[4], in[4];
+#pragma unroll
+      for (int j = 0; j < 2; j++)
+#pragma unroll
+        for (int i = 0; i < 2; i++) {
+          const int wx = (int)mx - 1 + i, wy = my - 1 + j;
+          ok[j * 2 + i] = (unsigned)wx < (unsigned)g.modX && (unsigned)wy < (unsigned)g.modY;
+          if (ok[j * 2 + i]) {
+            const unsigned off = (unsigned)((wy * g.modX + wx) * g.N) + nv * VEC;
+            vload<VEC>(gr_p + off, gr[j * 2 + i]);
+            vload<VEC>(ac_p + off, ac[j * 2 + i]);
+          }
+          const int X = 2 * (int)mx + g.px + i, Y = 2 * my + g.py + j;        // (a, b) = (i, j) for the patch's own elements
+          in[j * 2 + i] = (unsigned)X < (unsigned)g.W && (unsigned)Y < (unsigned)g.H;
+          if (in[j * 2 + i]) vload<VEC>(img + (unsigned)((Y * g.W + X) * g.N) + nv * VEC, im[j * 2 + i]);
+        }
+#pragma unroll
+      for (int b = 0; b < 2; b++)
+#pragma unroll
+        for (int a = 0; a < 2; a++) {
+          if (!in[b * 2 + a]) continue;
+          const int X = 2 * (int)mx + g.px + a, Y = 2 * my + g.py + b;
+          const unsigned idx = (unsigned)((Y * g.W + X) * g.N) + nv * VEC;
+          float acc[VEC], old[VEC];
+#pragma unroll
+          for (int v = 0; v < VEC; v++) { acc[v] = 0.f; old[v] = 0.f; }
+          if (st != 0.f) vload<VEC>(out + idx, old);
+#pragma unroll
+          for (int j = 0; j < 2; j++) {
+            if (2 * (1 - j) + b >= g.ky) continue;
+#pragma unroll
+            for (int i = 0; i < 2; i++) {
+              if (2 * (1 - i) + a >= g.kx || !ok[j * 2 + i]) continue;
+#pragma unroll
+              for (int v = 0; v < VEC; v++) acc[v] += (im[b * 2 + a][v] == ac[j * 2 + i][v]) ? so * gr[j * 2 + i][v] : 0.f;   // gemm.cu:291
+            }
+          }
+#pragma unroll
+          for (int v = 0; v < VEC; v++) acc[v] += st * old[v];
+          if (relu_mask) {
+            float mk[VEC];
+            if (mask_is_input) {
+#pragma unroll
+              for (int v = 0; v < VEC; v++) mk[v] = im[b * 2 + a][v];
+            } else vload<VEC>(mk_p + idx, mk);
+#pragma unroll
+            for (int v = 0; v < VEC; v++) acc[v] = mk[v] > 0.f ? acc[v] : 0.f;
+          }
+          vstore<VEC>(out + idx, acc);
+          if (out16) vemit<VEC>(out16 + idx, acc);
+          if (rowsum) {
+#pragma unroll
+            for (int v = 0; v < VEC; v++) total += acc[v];
+          }
+        }
+    }
+  }
+  if (rowsum) {
+    __shared__ float sh[8];
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = total;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+      for (int w = 0; w < 8; w++) s += sh[w];
+      rowsum[(size_t)blockIdx.x * gridDim.y + blockIdx.y] = s;
+    }
+  }
+}
+
 static int pow2_shift(unsigned v) { int s = 0; while ((1u << s) < v) s++; return (1u << s) == v ? s : -1; }
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
@@ -463,6 +652,12 @@ static unsigned long long pool_sig(const PoolGeom& g) {
   for (int v : {g.N, g.W, g.H, g.C, g.modX, g.modY, g.kx, g.ky, g.sx, g.sy, g.px, g.py}) sig = (sig ^ (unsigned)v) * 1099511628211ULL;
   return sig;
 }
+// CONVNET_B200_POOL_PATCH=0: the per-element undo kernels instead of the patch kernels (A/B measurements)
+static bool pool_patch_enabled() {
+  static const bool on = !(getenv("CONVNET_B200_POOL_PATCH") && getenv("CONVNET_B200_POOL_PATCH")[0] == '0');
+  return on;
+}
+
 static bool masks_supported(const PoolGeom& g) {      // the row kernels, windows up to 3 x 3 (9 tie bits + the sign bit)
   return g.kt == 1 && g.T == 1 && g.modT == 1 && std::max(g.kx, g.ky) <= 3 && g.sx == g.sy && (long long)g.N * g.W * g.H < (1LL << 31);
 }
@@ -533,16 +728,35 @@ static bool launch_undo(const PoolGeom& g, const float* images, const float* gra
     const int S = (g.sx == g.sy && g.sx <= 2) ? g.sx : 0;
     // the forward pass left tie masks for exactly this (input, output) pair and nothing wrote either since: no need to
     // reload and compare them.  A fused ReLU' mask is only expressible when it IS the pool input (bit 15 = maximum > 0).
-    if (MAX && q == 2 && std::max(g.kx, g.ky) == 3 && masks_supported(g) && (mask == nullptr || mask == images)) {
+    // (with scaleTargets != 0 the compare path also zeroes the OLD target where the mask fails; the tie masks cannot say
+    // that for elements that are no window's maximum, so that combination stays on the compare path)
+    if (MAX && q == 2 && std::max(g.kx, g.ky) == 3 && masks_supported(g) && (mask == nullptr || (mask == images && st == 0.f))) {
       const uint16_t* tm = pool_masks_find(acts, (long long)g.N * g.modX * g.modY * g.C, images, pool_sig(g));
       if (tm) {
-        if (colsum && colsum_slices) *colsum_slices = g.H;
         const int pos = mask != nullptr ? 1 : 0;
+        if (S == 2 && g.px <= 0 && g.py <= 0 && g.px >= -2 && g.py >= -2 && pool_patch_enabled()) {
+          // patches: element X belongs to patch (X - px) / 2; the first patch holds X = 0, the last X = W - 1
+          const int PX = (g.W - 1 - g.px) / 2 + 1, PY = (g.H - 1 - g.py) / 2 + 1;
+          const int shp = pow2_shift(g.N / VEC);
+          if (colsum && colsum_slices) *colsum_slices = PY;
+          pool_undo_masked_patch_kernel<VEC><<<dim3((unsigned)PY, planes), 256, 0, s>>>(g, grads, tm, targets, st, so, pos, shp, t16,
+                                                                                     colsum, PX, PY);
+          return t16 != nullptr;
+        }
+        if (colsum && colsum_slices) *colsum_slices = g.H;
         if (S == 2) pool_undo_masked_kernel<VEC, 2, 2, 3><<<rgrid, 256, 0, s>>>(g, grads, tm, targets, st, so, pos, sh, t16, colsum);
         else if (S == 1) pool_undo_masked_kernel<VEC, 2, 1, 3><<<rgrid, 256, 0, s>>>(g, grads, tm, targets, st, so, pos, sh, t16, colsum);
         else pool_undo_masked_kernel<VEC, 2, 0, 3><<<rgrid, 256, 0, s>>>(g, grads, tm, targets, st, so, pos, sh, t16, colsum);
         return t16 != nullptr;
       }
+    }
+    if (MAX && S == 2 && q == 2 && std::max(g.kx, g.ky) <= 3 && g.px <= 0 && g.py <= 0 && g.px >= -2 && g.py >= -2 &&
+        pool_patch_enabled()) {
+      const int PX = (g.W - 1 - g.px) / 2 + 1, PY = (g.H - 1 - g.py) / 2 + 1;
+      if (colsum && colsum_slices) *colsum_slices = PY;
+      pool_undo_patch_kernel<VEC><<<dim3((unsigned)PY, planes), 256, 0, s>>>(g, images, grads, acts, targets, st, so, mask, sh, t16,
+                                                                          colsum, PX, PY);
+      return t16 != nullptr;
     }
     if (colsum && colsum_slices) *colsum_slices = g.H;
 #define CNB_POOL_UNDO(QQ, SS) pool_undo_rows_kernel<VEC, MAX, QQ, SS><<<rgrid, 256, 0, s>>>(g, images, grads, acts, targets, st, so, mask, sh, t16, colsum)

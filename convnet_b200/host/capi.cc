@@ -53,6 +53,12 @@ API void cnb_net_update(void* p) { ((NetHandle*)p)->net->UpdateWeights(); }
 API float cnb_net_loss(void* p) { return ((NetHandle*)p)->net->GetLoss(); }
 // one training step; *loss (may be NULL) receives the summed cross-entropy of the batch (one scalar D2H, like GetLoss)
 API void cnb_net_train_step(void* p, float* loss) { ((NetHandle*)p)->net->TrainOneBatch(loss); }
+// one traced training step (ConvNet::TraceStep); returns the number of floats the full record has, writes min(cap, that)
+API int cnb_net_trace_step(void* p, float* out, int cap) {
+  const std::vector<float> t = ((NetHandle*)p)->net->TraceStep();
+  for (int i = 0; i < cap && i < (int)t.size(); i++) out[i] = t[i];
+  return (int)t.size();
+}
 
 // data parallel: rank 0 calls cnb_dp_unique_id, the launcher broadcasts the 128 bytes, every rank calls cnb_net_dp_init
 API int cnb_dp_unique_id(char* out128) { return DataParallelSync::GetUniqueId(out128) ? 0 : -1; }

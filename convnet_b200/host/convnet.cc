@@ -222,11 +222,15 @@ void ConvNet::InvalidateStaging() { convnet_b200_bf16_invalidate(nullptr); }
 ConvNet::~ConvNet() {
   if (comm_) { cudaStreamSynchronize(comm_); cudaStreamDestroy(comm_); }
   if (side_) { cudaStreamSynchronize(side_); cudaStreamDestroy(side_); }
+  if (opt_) { cudaStreamSynchronize(opt_); cudaStreamDestroy(opt_); }
+  if (ev_opt_) cudaEventDestroy(ev_opt_);
   if (ev_comm_) cudaEventDestroy(ev_comm_);
   for (cudaEvent_t e : ev_reduced_) cudaEventDestroy(e);
   if (ev_main_) cudaEventDestroy(ev_main_);
   if (ev_side_) cudaEventDestroy(ev_side_);
   if (lane_.ready) cudaEventDestroy(lane_.ready);
+  for (cudaEvent_t e : {trace_.t0, trace_.fwd, trace_.bwd, trace_.end}) if (e) cudaEventDestroy(e);
+  for (std::vector<cudaEvent_t>* v : {&trace_.c0, &trace_.c1, &trace_.s1}) for (cudaEvent_t e : *v) cudaEventDestroy(e);
   convnet_b200_reserve_sms(0);
   convnet_b200_bf16_invalidate(nullptr);                     // the buffers go away; a later net may get the same addresses
   for (Edge* e : edges_) delete e;
@@ -263,6 +267,8 @@ void ConvNet::AllocateMemory() {
   HOST_CUDA_CHECK(cudaStreamSynchronize(Matrix::Stream()));
   InvalidateStaging();
   HOST_CUDA_CHECK(cudaStreamCreateWithFlags(&side_, cudaStreamNonBlocking));
+  HOST_CUDA_CHECK(cudaStreamCreateWithFlags(&opt_, cudaStreamNonBlocking));
+  HOST_CUDA_CHECK(cudaEventCreateWithFlags(&ev_opt_, cudaEventDisableTiming));
   HOST_CUDA_CHECK(cudaStreamCreateWithFlags(&comm_, cudaStreamNonBlocking));
   HOST_CUDA_CHECK(cudaEventCreateWithFlags(&ev_comm_, cudaEventDisableTiming));
   HOST_CUDA_CHECK(cudaEventCreateWithFlags(&ev_main_, cudaEventDisableTiming));
@@ -331,8 +337,10 @@ void ConvNet::Bprop() {                                      // convnet.cc:390-4
         HOST_CUDA_CHECK(cudaStreamWaitEvent(comm_, ev_main_, 0));
         HOST_CUDA_CHECK(cudaEventRecord(ev_side_, side_));
         HOST_CUDA_CHECK(cudaStreamWaitEvent(comm_, ev_side_, 0));
+        if (trace_.on) HOST_CUDA_CHECK(cudaEventRecord(trace_.c0[bi], comm_));
         dp_->AllReduceAverageAsync(grad_parameters_.GetDevData(), b.lo, b.hi - b.lo, comm_);
         HOST_CUDA_CHECK(cudaEventRecord(ev_reduced_[bi], comm_));
+        if (trace_.on) HOST_CUDA_CHECK(cudaEventRecord(trace_.c1[bi], comm_));
         comm_pending_ = true;
       }
     if (!in->IsInput()) {
@@ -356,27 +364,31 @@ void ConvNet::Bprop() {                                      // convnet.cc:390-4
     if (eager_update_)
       for (size_t bi = 0; bi < buckets_.size(); bi++)
         if (buckets_[bi].trigger == i - 1) {
-          if (dp_ && dp_->world() > 1) HOST_CUDA_CHECK(cudaStreamWaitEvent(side_, ev_reduced_[bi], 0));   // SGD after its all-reduce
+          if (dp_ && dp_->world() > 1) HOST_CUDA_CHECK(cudaStreamWaitEvent(opt_, ev_reduced_[bi], 0));   // SGD after its all-reduce
           IssueBucketUpdate(buckets_[bi]);
+          if (trace_.on) HOST_CUDA_CHECK(cudaEventRecord(trace_.s1[bi], opt_));
         }
   }
   if (!eager_update_ && !(dp_ && dp_->world() > 1)) WaitSide();   // stand-alone Bprop: the gradients are complete on return
 }
 
-// the SGD step of one bucket on the side stream, after (stream order) that bucket's all-reduce and after (event) the
-// compute stream has finished reading the bucket's weights in this step
+// the SGD step of one bucket on the optimizer stream, after (events) that bucket's all-reduce, the bias-gradient sums
+// queued on the side stream so far, and the compute stream's last read of the bucket's weights in this step.  Its own
+// stream: an all-reduce waits for the side stream's bias gradients, and must not queue behind an earlier bucket's SGD step
 void ConvNet::IssueBucketUpdate(const Bucket& b) {
   std::vector<CnbSgdTensor> tensors;
   for (int i = b.trigger; i <= b.last; i++)
     if (EdgeWithWeight* w = dynamic_cast<EdgeWithWeight*>(edges_[i])) w->AppendSgdTensors(tensors);
   if (tensors.empty()) return;
   HOST_CUDA_CHECK(cudaEventRecord(ev_main_, Matrix::Stream()));
-  HOST_CUDA_CHECK(cudaStreamWaitEvent(side_, ev_main_, 0));
+  HOST_CUDA_CHECK(cudaStreamWaitEvent(opt_, ev_main_, 0));
+  HOST_CUDA_CHECK(cudaEventRecord(ev_side_, side_));
+  HOST_CUDA_CHECK(cudaStreamWaitEvent(opt_, ev_side_, 0));
   void* main_stream = convnet_b200_get_stream();
-  convnet_b200_set_stream(side_);
+  convnet_b200_set_stream(opt_);
   cnb_sgd_momentum_multi(tensors.data(), (int)tensors.size());
   convnet_b200_set_stream(main_stream);
-  side_pending_ = true;
+  opt_pending_ = true;
 }
 void ConvNet::WaitSide() {
   if (lane_.used) { side_pending_ = true; lane_.used = false; }
@@ -385,6 +397,11 @@ void ConvNet::WaitSide() {
     HOST_CUDA_CHECK(cudaStreamWaitEvent(Matrix::Stream(), ev_comm_, 0));
     comm_pending_ = false;
     convnet_b200_reserve_sms(0);
+  }
+  if (opt_pending_) {
+    HOST_CUDA_CHECK(cudaEventRecord(ev_opt_, opt_));
+    HOST_CUDA_CHECK(cudaStreamWaitEvent(Matrix::Stream(), ev_opt_, 0));
+    opt_pending_ = false;
   }
   if (!side_pending_) return;
   HOST_CUDA_CHECK(cudaEventRecord(ev_side_, side_));
@@ -403,19 +420,49 @@ void ConvNet::UpdateWeights() {                              // convnet.cc:440-4
 }
 
 void ConvNet::TrainOneBatch(float* loss_out) {               // convnet.cc:475-485 (GetBatch is the caller's H2D copy)
+  if (trace_.on) HOST_CUDA_CHECK(cudaEventRecord(trace_.t0, Matrix::Stream()));
   Fprop(true);
   ComputeDeriv();
+  if (trace_.on) HOST_CUDA_CHECK(cudaEventRecord(trace_.fwd, Matrix::Stream()));
   if (loss_out) {                                            // GetLoss: one scalar D2H per step, like the reference
     cnb_sum(OutputLayer().GetLossPerImage(), loss_sum_.GetDevData(), batch_size_);
   }
   static const bool no_eager = getenv("CONVNET_B200_NO_EAGER_UPDATE") && getenv("CONVNET_B200_NO_EAGER_UPDATE")[0] == '1';
   eager_update_ = !no_eager;
   Bprop();
+  if (trace_.on) HOST_CUDA_CHECK(cudaEventRecord(trace_.bwd, Matrix::Stream()));
   updated_in_bprop_ = eager_update_;
   eager_update_ = false;
   UpdateWeights();
+  if (trace_.on) HOST_CUDA_CHECK(cudaEventRecord(trace_.end, Matrix::Stream()));
   if (loss_out) *loss_out = loss_sum_.ReadValue(0);
   step_++;
+}
+
+std::vector<float> ConvNet::TraceStep() {
+  auto make = [](cudaEvent_t* e) { if (!*e) HOST_CUDA_CHECK(cudaEventCreate(e)); };
+  make(&trace_.t0); make(&trace_.fwd); make(&trace_.bwd); make(&trace_.end);
+  for (std::vector<cudaEvent_t>* v : {&trace_.c0, &trace_.c1, &trace_.s1})
+    while (v->size() < buckets_.size()) { cudaEvent_t e = nullptr; make(&e); v->push_back(e); }
+  HOST_CUDA_CHECK(cudaStreamSynchronize(Matrix::Stream()));
+  trace_.on = true;
+  TrainOneBatch(nullptr);
+  trace_.on = false;
+  HOST_CUDA_CHECK(cudaStreamSynchronize(Matrix::Stream()));
+  HOST_CUDA_CHECK(cudaStreamSynchronize(side_));
+  HOST_CUDA_CHECK(cudaStreamSynchronize(opt_));
+  HOST_CUDA_CHECK(cudaStreamSynchronize(comm_));
+  auto since = [&](cudaEvent_t e) { float ms = -1.f; return cudaEventElapsedTime(&ms, trace_.t0, e) == cudaSuccess ? ms : -1.f; };
+  std::vector<float> out = {since(trace_.fwd), since(trace_.bwd), since(trace_.end), (float)buckets_.size()};
+  const bool multi = dp_ && dp_->world() > 1;
+  for (size_t bi = 0; bi < buckets_.size(); bi++) {
+    out.push_back((float)((buckets_[bi].hi - buckets_[bi].lo) * 4.0 / 1e6));
+    out.push_back(multi ? since(trace_.c0[bi]) : -1.f);
+    out.push_back(multi ? since(trace_.c1[bi]) : -1.f);
+    out.push_back(since(trace_.s1[bi]));
+  }
+  cudaGetLastError();
+  return out;
 }
 
 std::vector<Bucket> PlanBuckets(const std::vector<size_t>& edge_offset, const std::vector<size_t>& edge_size,

@@ -133,6 +133,10 @@ class ConvNet {
   const std::vector<size_t>& EdgeOffsets() const { return edge_offset_; }
   const std::vector<size_t>& EdgeSizes() const { return edge_size_; }
   float* DeviceLoss() { return loss_sum_.GetDevData(); }
+  // One traced TrainOneBatch: device times (ms since the step began) of the pipeline's milestones, for the scaling report:
+  // {fprop_end, bprop_compute_end, step_end, n_buckets, then per bucket {MB, exchange_begin, exchange_end, sgd_end}}.
+  // exchange_* are -1 on one rank.  The events cost a few microseconds; the ordinary step records none of them.
+  std::vector<float> TraceStep();
 
  protected:
   ModelConfig model_;
@@ -149,15 +153,21 @@ class ConvNet {
   void WaitSide();
   DataParallelSync* dp_ = nullptr;
   std::vector<Bucket> buckets_;
-  // side_: bias-gradient passes and the per-bucket SGD steps; comm_: the NCCL all-reduces only, so that a long exchange
-  // (fc6: 302 MB) never delays the column sums or the optimizer steps of other buckets queued behind it
-  cudaStream_t side_ = nullptr, comm_ = nullptr;
-  cudaEvent_t ev_main_ = nullptr, ev_side_ = nullptr, ev_comm_ = nullptr;
+  // side_: bias-gradient passes; comm_: the NCCL all-reduces only; opt_: the per-bucket SGD steps.  Three streams so that a
+  // long exchange (fc6: 302 MB) never delays the column sums, and an all-reduce (which waits for the side stream's bias
+  // gradients) never queues behind the optimizer step of an earlier bucket
+  cudaStream_t side_ = nullptr, comm_ = nullptr, opt_ = nullptr;
+  cudaEvent_t ev_main_ = nullptr, ev_side_ = nullptr, ev_comm_ = nullptr, ev_opt_ = nullptr;
   std::vector<cudaEvent_t> ev_reduced_;         // per bucket: its all-reduce has finished (comm_ -> side_ / main)
   bool comm_pending_ = false;
   SideLane lane_;                               // what the edges see of the side stream (bias-gradient passes)
-  bool eager_update_ = false, side_pending_ = false, updated_in_bprop_ = false;
+  bool eager_update_ = false, side_pending_ = false, opt_pending_ = false, updated_in_bprop_ = false;
   bool dropout_active_ = false;                 // the last Fprop applied dropout (train == true): states hold relu(x) * mask
+  struct Trace {
+    bool on = false;
+    cudaEvent_t t0 = nullptr, fwd = nullptr, bwd = nullptr, end = nullptr;
+    std::vector<cudaEvent_t> c0, c1, s1;        // per bucket: exchange begin / end (comm_), optimizer step end (side_)
+  } trace_;
   unsigned long long step_ = 0;
   unsigned long long dropout_salt_ = 0xD1B54A32D192ED03ULL;      // model seed and data-parallel rank, see SetDataParallel
 };

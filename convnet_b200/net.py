@@ -29,6 +29,7 @@ def load_host():
             "cnb_net_num_layers": ([vp], i), "cnb_net_device_loss": ([vp], vp),
             "cnb_net_fprop": ([vp, i], None), "cnb_net_bprop": ([vp], None), "cnb_net_update": ([vp], None),
             "cnb_net_loss": ([vp], f), "cnb_net_train_step": ([vp, ct.POINTER(f)], None),
+            "cnb_net_trace_step": ([vp, ct.POINTER(f), i], i),
             "cnb_dp_unique_id": ([ct.c_char_p], i), "cnb_net_dp_init": ([vp, i, i, ct.c_char_p, ll], i),
             "cnb_plan_buckets": ([i, ct.POINTER(ll), ct.POINTER(ll), ll, i, ct.POINTER(ll), ct.POINTER(ll), ct.POINTER(i)], i),
             "cnb_model_edge_params": ([ct.c_char_p, i, i, ct.POINTER(ll)], i),
@@ -117,6 +118,18 @@ class Net:
             return v.value
         self.H.cnb_net_train_step(self.h, None)
         return None
+
+    def trace_step(self):
+        """One extra training step with timing events on the three streams (ConvNet::TraceStep): device milliseconds since
+        the step began of the pipeline's milestones, and per gradient bucket its size, exchange window and SGD end."""
+        buf = (ct.c_float * 512)()
+        n = min(512, self.H.cnb_net_trace_step(self.h, buf, 512))
+        v = [buf[k] for k in range(n)]
+        out = {"fprop_end_ms": v[0], "bprop_compute_end_ms": v[1], "step_end_ms": v[2], "buckets": []}
+        for b in range(int(v[3])):
+            mb, c0, c1, s1 = v[4 + 4 * b:8 + 4 * b]
+            out["buckets"].append({"MB": round(mb, 3), "exchange_begin_ms": c0, "exchange_end_ms": c1, "sgd_end_ms": s1})
+        return out
 
     def dp_init(self, rank, world, id_bytes, bucket_floats=8 << 20):
         assert len(id_bytes) == 128

@@ -75,11 +75,13 @@ def test_library_writes_keep_copies_coherent():
         lib.set_precision("fp32")
 
 
-@pytest.mark.parametrize("shape", [(128, 27, 27, 64), (32, 110, 110, 8), (7, 9, 9, 5)])
-def test_max_pool_undo_from_tie_masks_is_bit_identical(shape):
+@pytest.mark.parametrize("pad", [1, 0])
+@pytest.mark.parametrize("shape", [(128, 27, 27, 64), (32, 110, 110, 8), (7, 9, 9, 5), (4, 8, 8, 3)])
+def test_max_pool_undo_from_tie_masks_is_bit_identical(shape, pad):
     """convnet_b200_pool_cache_next: the undo fed by the forward pass's tie masks equals the compare-based undo bit for bit —
-    with ties (quantised inputs), with scaleTargets, with the fused ReLU' mask that is the pool input, and it falls back as
-    soon as the library writes one of the two tensors."""
+    with ties (quantised inputs), with scaleTargets, with the fused ReLU' mask that is the pool input (that mask together
+    with scaleTargets != 0 stays on the compare path), odd and even widths, with and without padding — and it falls back
+    as soon as the library writes one of the two tensors."""
     import torch
     from convnet_b200 import conv_gemm as cg
     from convnet_b200 import lib
@@ -87,8 +89,8 @@ def test_max_pool_undo_from_tie_masks_is_bit_identical(shape):
     from convnet_b200.matrix import CUDAMatrix
     L = lib.load()
     N, W, H, C = shape
-    mod = num_modules(W, 3, 2, 1)
-    d = GetConvDesc(C, C, 3, 3, 2, 2, 1, 1)
+    mod = num_modules(W, 3, 2, pad)
+    d = GetConvDesc(C, C, 3, 3, 2, 2, pad, pad)
     ish, psh = (N, W, H, C), (N, mod, mod, C)
     g = torch.Generator(device="cuda").manual_seed(4)
     x = CUDAMatrix(N, W * H * C, ish)
