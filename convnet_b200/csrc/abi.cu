@@ -50,15 +50,25 @@ void conv_up(const ConvGeom& g, const float* images, const float* filters, float
   CNB_REQUIRE(!fuse.bias_grad, "convUp: a fused bias gradient belongs to a backward call");
   Emit emit(targets, g.out_total, fuse.emit_bf16 != 0);
   emit.attach(fuse);
+  bool dropped = false;
+  fuse.dropped = &dropped;
   if (!(state().precision != kPrecFP32 && tc_conv_up(g, images, filters, targets, st, so, fuse))) {
     simt_conv_up(g, images, filters, targets, st, so, fuse);
     state().last_conv_path = kPathSimt;
+  }
+  if (fuse.drop_scale != 0.f && !dropped) {        // the kernel could not apply the dropout: one pass, which also (re)writes the bf16 twin
+    dropout_apply(targets, g.out_total, fuse.drop_prob, fuse.drop_scale, fuse.drop_seed, emit.buf);
+    if (emit.buf) emit.done = true;
   }
   emit.finish();
 }
 
 void conv_down(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float st, float so) {
   Fuse fuse = take_fuse();
+  if (fuse.prestage) {                             // filters-only preparation of this call (convnet_b200_prestage_next)
+    if (state().precision != kPrecFP32) tc_conv_down_prestage(g, derivs, filters);
+    return;
+  }
   so *= fuse.out_scale;
   // the mask can ride in the epilogue only when one launch produces the final value of every target element
   const bool whole = g.conv && g.frames == 1 && g.cin0 == 0 && g.Cin == g.CinT;

@@ -46,6 +46,15 @@ namespace cnb {
   abort();
 }
 
+// the dropout generator: a counter-based hash (splitmix64 finaliser) of seed + element index, top 32 bits -> [0, 1)
+__host__ __device__ __forceinline__ uint32_t hash_u32(unsigned long long x) {
+  x += 0x9E3779B97F4A7C15ULL; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL; x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
+  return (uint32_t)((x ^ (x >> 31)) >> 32);
+}
+__host__ __device__ __forceinline__ float dropout_keep(unsigned long long x, float dropprob, float scale) {
+  return hash_u32(x) * (1.0f / 4294967296.0f) >= dropprob ? scale : 0.f;
+}
+
 // ---- global state (one host thread per process/GPU, like the reference) -------------
 enum Precision { kPrecFP32 = 0, kPrecTF32 = 1, kPrecBF16 = 2 };
 enum ConvPath { kPathNone = -1, kPathSimt = 0, kPathTcTf32 = 1, kPathTcBf16 = 2 };
@@ -55,6 +64,11 @@ struct Fuse {
   const float* bias = nullptr;       // fprop: + bias[output channel]
   int relu = 0;                      // fprop: max(., 0) after the bias
   const float* relu_mask = nullptr;  // dgrad / pool undo: result zeroed where relu_mask <= 0 (same shape as the target)
+  // fprop: dropout after bias / ReLU (convnet_b200_fuse_next_dropout): element i (its index in the target tensor) is kept
+  // iff dropout_uniform(seed + i) >= drop_prob, kept values are multiplied by drop_scale; drop_scale == 0: no dropout
+  float drop_prob = 0.f, drop_scale = 0.f; unsigned long long drop_seed = 0;
+  bool* dropped = nullptr;           // internal: the kernel sets it when it applied the dropout itself
+  int prestage = 0;                  // convDown*: only build what the call can prepare from the FILTERS (convnet_b200_prestage_next)
   int pool_cache = 0;                // MaxPool*: also record the tie masks for the matching MaxPoolUndo* (convnet_b200_pool_cache_next)
   float out_scale = 1.f;             // dgrad: result multiplied by this (the kept-unit scale of a dropout layer, see ext.h)
   int emit_bf16 = 0;                 // any writer: also leave a staged bf16 copy of the whole target (convnet_b200_emit_bf16_next)
@@ -64,7 +78,7 @@ struct Fuse {
   // internal (filled by the ABI wrapper): where the bf16 twin of the target goes; a kernel that writes it sets *emitted
   __nv_bfloat16* out16 = nullptr;
   bool* emitted = nullptr;
-  bool any() const { return bias || relu || relu_mask; }
+  bool any() const { return bias || relu || relu_mask || drop_scale != 0.f; }
 };
 
 struct State {

@@ -75,6 +75,9 @@ struct TcParams {
   float st, so;
   const float* bias; int relu;      // fused fprop epilogue: + bias[o], then max(., 0)
   const float* mask;                // fused dgrad epilogue: zero where mask <= 0 (same layout as out)
+  // fast fprop epilogue: dropout of the (bias + ReLU'd) result, element index = offset from `out` (Fuse::drop_*); 0 = none
+  float drop_prob, drop_scale;
+  unsigned long long drop_seed;
   long long out_frame_step;         // fprop: floats between output frames
   uint32_t idesc;
   // fast kernels (tc_fast_kernel): bf16, one-request A tiles, K per pipeline stage = 16 * ksteps elements
@@ -977,10 +980,13 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
           for (int j = 0; j < 32; j++) bv[j] = bp ? __ldg(bp + j) : 0.f;
           const bool relu = p.relu != 0;
           if (p.mask == nullptr) {
+            const bool drop = p.drop_scale != 0.f;
+            unsigned long long ctr = p.drop_seed + (unsigned long long)(dst - p.out);      // seed + element index
 #pragma unroll
             for (int j = 0; j < 32; j++) {
               float r = fmaf(p.so, v[j], bv[j]);
               r = relu ? fmaxf(r, 0.f) : r;
+              if (drop) { r *= dropout_keep(ctr, p.drop_prob, p.drop_scale); ctr += (unsigned long long)col_stride; }
               *dst = r;
               if (dst16) { *dst16 = __float2bfloat16_rn(r); dst16 += col_stride; }
               dst += col_stride;
@@ -1249,6 +1255,7 @@ void fill_common(TcParams& p, const ConvGeom& g, const Elem& e) {
   static const int dbg = getenv("CONVNET_B200_TC_DEBUG") ? atoi(getenv("CONVNET_B200_TC_DEBUG")) : 0;
   p.dbg = dbg;
   p.bias = nullptr; p.relu = 0; p.mask = nullptr; p.out16 = nullptr;
+  p.drop_prob = 0.f; p.drop_scale = 0.f; p.drop_seed = 0;
   p.o_sx = p.o_sy = 1; p.o_x0 = p.o_y0 = 0; p.o_W = g.modX; p.out_plane = g.modules;
   p.ksteps = 4; p.a_stage_bytes = kAStageBytes; p.b_chunks = 0;
   p.out_frame_step = g.out_frame_step;
@@ -1469,7 +1476,14 @@ static bool tc_conv_up_impl(const ConvGeom& g, const float* images, const float*
         const int box[3] = {64, 1, e2.bk};
         ok = make_map(&fb, flt, e2, 3, dims, str, box, true);
       }
-      if (ok) { launch_fast<kFprop>(fa, fb, f); done = true; }
+      if (ok) {
+        // dropout in the epilogue: the element index is the offset from the start of the WHOLE target tensor
+        const bool drop = fuse.drop_scale != 0.f && g.cout0 == 0 && g.Cout == g.CoutT;
+        if (drop) { f.drop_prob = fuse.drop_prob; f.drop_scale = fuse.drop_scale; f.drop_seed = fuse.drop_seed; }
+        launch_fast<kFprop>(fa, fb, f);
+        done = true;
+        if (drop && fuse.dropped) *fuse.dropped = true;
+      }
     }
   }
   // tf32 x mode (RGB first layer) on the lean kernel: one k-block per channel = 8 x 8 taps
@@ -1512,16 +1526,28 @@ bool tc_conv_up(const ConvGeom& g, const float* images, const float* filters, fl
 // flavour of tc_fast_kernel: CTA pairs, both operands MN-major, no dead taps.  The gather kernel above, with its K-major B
 // of 256 rows per k-block per CTA, measured L2-feed-bound at 0.2-0.4 of the fprop rate on the same problem
 // (profiles/r2_layer_probe_fast_v1.log).  One launch per stride phase; the epilogue writes every sx-th / sy-th pixel.
-static bool tc_conv_down_as_fprop(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float so,
-                                  const Fuse& fuse) {
+// does the phase-decomposed dgrad (below) take this call?  `banks` receives the phases
+static bool dgrad_as_fprop_eligible(const ConvGeom& g, const float* derivs, const float* filters, DgradBanks* banks) {
   static const bool off = getenv("CONVNET_B200_NO_DGRAD_AS_FPROP") && getenv("CONVNET_B200_NO_DGRAD_AS_FPROP")[0] == '1';
   if (off || !fast_enabled() || !g.conv || g.frames != 1) return false;
   if (g.cin0 != 0 || g.Cin != g.CinT || g.cout0 != 0 || g.Cout != g.CoutT) return false;
   if (g.N % 128 != 0 || g.Cin % 32 != 0 || g.Cout % 8 != 0 || !aligned16(derivs) || !aligned16(filters)) return false;
   if ((long long)g.N * g.W * g.H < 1024) return false;                      // FC-shaped: weight-streaming bound, stays tf32
+  if (dgrad_phases(g, banks) <= 0) return false;
+  for (int i = 0; i < banks->count; i++) if (banks->phase[i].ku == 0 || banks->phase[i].kv == 0) return false;
+  return true;
+}
+
+void tc_conv_down_prestage(const ConvGeom& g, const float* derivs, const float* filters) {
   DgradBanks banks;
-  if (dgrad_phases(g, &banks) <= 0) return false;
-  for (int i = 0; i < banks.count; i++) if (banks.phase[i].ku == 0 || banks.phase[i].kv == 0) return false;
+  if (!tc_enabled() || !g.conv || !want_bf16() || !dgrad_as_fprop_eligible(g, derivs, filters, &banks)) return;
+  dgrad_weights(filters, g, banks);
+}
+
+static bool tc_conv_down_as_fprop(const ConvGeom& g, const float* derivs, const float* filters, float* targets, float so,
+                                  const Fuse& fuse) {
+  DgradBanks banks;
+  if (!dgrad_as_fprop_eligible(g, derivs, filters, &banks)) return false;
   const Elem e = elem_for(true);
   // the derivative as bf16 (staged by the producer, or converted here)
   const __nv_bfloat16* sd = bf16_staged(derivs, g.out_total);

@@ -147,10 +147,6 @@ __global__ void __launch_bounds__(256) sgd_multi_kernel(const __grid_constant__ 
   }
 }
 
-__device__ __forceinline__ uint32_t hash_u32(unsigned long long x) {     // splitmix64 finaliser
-  x += 0x9E3779B97F4A7C15ULL; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL; x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;
-  return (uint32_t)((x ^ (x >> 31)) >> 32);
-}
 // n4 float4 groups (vector body) + scalar tail, like relu_kernel; element i always draws from hash(seed + i)
 __global__ void dropout_kernel(float* x, float* mask, long long n, long long n4, float dropprob, float scale,
                                unsigned long long seed, __nv_bfloat16* out16) {
@@ -163,14 +159,14 @@ __global__ void dropout_kernel(float* x, float* mask, long long n, long long n4,
     m.z = hash_u32(b + 2) * (1.0f / 4294967296.0f) >= dropprob ? scale : 0.f;
     m.w = hash_u32(b + 3) * (1.0f / 4294967296.0f) >= dropprob ? scale : 0.f;
     v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
-    reinterpret_cast<float4*>(mask)[i] = m;
+    if (mask) reinterpret_cast<float4*>(mask)[i] = m;
     reinterpret_cast<float4*>(x)[i] = v;
     emit4(out16, i, v);
   }
   for (long long i = 4 * n4 + tid; i < n; i += nt) {
     const float u = hash_u32(seed + (unsigned long long)i) * (1.0f / 4294967296.0f);
     const float m = u >= dropprob ? scale : 0.f;
-    mask[i] = m;
+    if (mask) mask[i] = m;
     const float v = x[i] * m;
     x[i] = v;
     if (out16) out16[i] = __float2bfloat16_rn(v);
@@ -240,6 +236,14 @@ void colsum_finish(const float* part, float* grad_bias, int cols, int slices, fl
   CNB_LAUNCH_CHECK("colsum_finish");
 }
 
+// dropout without a mask tensor, writing the bf16 twin when given: the fallback of convnet_b200_fuse_next_dropout for calls
+// whose kernel cannot apply it in the epilogue (the caller owns the staging bookkeeping of x)
+void dropout_apply(float* x, long long n, float dropprob, float scale, unsigned long long seed, __nv_bfloat16* out16) {
+  if (n <= 0) return;
+  const long long n4 = aligned16(x) ? n / 4 : 0;
+  dropout_kernel<<<blocks_for(std::max(n4, n - 4 * n4), 256), 256, 0, state().stream>>>(x, nullptr, n, n4, dropprob, scale, seed, out16);
+  count_launch(); CNB_LAUNCH_CHECK("dropout_apply");
+}
 }  // namespace cnb
 
 using namespace cnb;

@@ -84,6 +84,11 @@ void convnet_b200_fuse_next_bias_grad(float* grad_bias, float scaleTargets, floa
 }
 void convnet_b200_fuse_next_scale(float scale) { state().fuse.out_scale = scale; }
 void convnet_b200_pool_cache_next(void) { state().fuse.pool_cache = 1; }
+void convnet_b200_prestage_next(void) { state().fuse.prestage = 1; }
+void convnet_b200_fuse_next_dropout(float dropprob, float scale, unsigned long long seed) {
+  Fuse& f = state().fuse;
+  f.drop_prob = dropprob; f.drop_scale = scale; f.drop_seed = seed;
+}
 void convnet_b200_reserve_sms(int n) { state().sm_reserve = n > 0 ? n : 0; }
 void convnet_b200_bf16_stage(const float* ptr, long long n) { bf16_stage(ptr, n); }
 void convnet_b200_bf16_ensure(const float* ptr, long long n) { bf16_ensure(ptr, n); }

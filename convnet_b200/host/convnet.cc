@@ -69,9 +69,12 @@ void Layer::ApplyDropout(bool train, unsigned long long step, unsigned long long
   if (emit) convnet_b200_emit_bf16_next();
   // salt = model seed and data-parallel rank (the reference seeds each process with seed + rank, convnet.cc:67-68):
   // replicas must not draw the same mask for the same local image index
-  const unsigned long long seed = (std::hash<std::string>()(config_.name) ^ (step * 0x9E3779B97F4A7C15ULL)) ^ salt;
+  const unsigned long long seed = DropoutSeed(step, salt);
   cnb_dropout(state_.GetDevData(), dropout_mask_.GetDevData(), (long long)state_.GetNumEls(), config_.dropprob,
               1.0f / (1.0f - config_.dropprob), seed);
+}
+unsigned long long Layer::DropoutSeed(unsigned long long step, unsigned long long salt) const {
+  return (std::hash<std::string>()(config_.name) ^ (step * 0x9E3779B97F4A7C15ULL)) ^ salt;
 }
 void Layer::ApplyDerivativeofDropout(bool emit) {
   if (config_.dropprob <= 0 || config_.is_input) return;
@@ -90,6 +93,7 @@ struct NcclApi {
   void* handle = nullptr;
   ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
   ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommInitRankConfig)(ncclComm_t*, int, ncclUniqueId, int, ncclConfig_t*) = nullptr;
   ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
   ncclResult_t (*AllReduce)(const void*, void*, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Bcast)(const void*, void*, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
@@ -106,6 +110,7 @@ NcclApi& nccl() {
     if (!api.handle) { fprintf(stderr, "convnet_b200 host: cannot load libnccl.so.2: %s\n", dlerror()); return api; }
 #define LOAD(field, sym) api.field = reinterpret_cast<decltype(api.field)>(dlsym(api.handle, sym))
     LOAD(GetUniqueId, "ncclGetUniqueId"); LOAD(CommInitRank, "ncclCommInitRank"); LOAD(CommDestroy, "ncclCommDestroy");
+    LOAD(CommInitRankConfig, "ncclCommInitRankConfig");
     LOAD(AllReduce, "ncclAllReduce"); LOAD(Bcast, "ncclBroadcast"); LOAD(GetErrorString, "ncclGetErrorString");
 #undef LOAD
     api.ok = api.GetUniqueId && api.CommInitRank && api.AllReduce && api.Bcast;
@@ -143,17 +148,27 @@ bool DataParallelSync::Init(int rank, int world, const char idbytes[128]) {
   rank_ = rank; world_ = world;
   ncclUniqueId id;
   memcpy(&id, idbytes, 128);
-  // the collective's CTAs run beside persistent conv kernels that own every SM they touch: keep NCCL narrow and let the
-  // conv grids leave exactly that many SMs free while a collective is in flight (convnet_b200_reserve_sms)
+  // The collective's CTAs need whole SMs (registers, shared memory) beside persistent conv kernels that own every SM they
+  // touch and walk their tiles with a fixed stride: a conv CTA that finds its SM taken starts late and stretches the whole
+  // kernel.  So NCCL gets exactly CONVNET_B200_NCCL_CTAS CTAs — through the communicator's own config, which holds whether or
+  // not the launcher (torch.distributed) initialised NCCL and its environment cache first — and the conv grids leave that
+  // many SMs free while a collective is in flight (convnet_b200_reserve_sms).  0: NCCL's default width, nothing reserved.
   const char* e = getenv("CONVNET_B200_NCCL_CTAS");
-  nccl_ctas_ = e ? atoi(e) : 8;
-  if (nccl_ctas_ > 0 && !getenv("NCCL_MAX_CTAS")) {
-    char buf[16]; snprintf(buf, sizeof(buf), "%d", nccl_ctas_);
-    setenv("NCCL_MAX_CTAS", buf, 1);
-  }
+  nccl_ctas_ = e ? atoi(e) : 16;
   if (nccl_ctas_ < 0) nccl_ctas_ = 0;
   ncclComm_t c;
-  NCCL_CHECK(nccl().CommInitRank(&c, world, id, rank));
+  if (nccl_ctas_ > 0 && nccl().CommInitRankConfig) {
+    ncclConfig_t cfg = NCCL_CONFIG_INITIALIZER;
+    cfg.minCTAs = nccl_ctas_;
+    cfg.maxCTAs = nccl_ctas_;
+    NCCL_CHECK(nccl().CommInitRankConfig(&c, world, id, rank, &cfg));
+  } else {
+    if (nccl_ctas_ > 0 && !getenv("NCCL_MAX_CTAS")) {          // older NCCL: the environment, effective only if nothing read it yet
+      char buf[16]; snprintf(buf, sizeof(buf), "%d", nccl_ctas_);
+      setenv("NCCL_MAX_CTAS", buf, 1);
+    }
+    NCCL_CHECK(nccl().CommInitRank(&c, world, id, rank));
+  }
   comm_ = c;
   HOST_CUDA_CHECK(cudaStreamCreateWithFlags(&comm_stream_, cudaStreamNonBlocking));
   HOST_CUDA_CHECK(cudaEventCreateWithFlags(&ready_, cudaEventDisableTiming));
@@ -292,12 +307,24 @@ void ConvNet::Fprop(bool train) {                            // convnet.cc:377-3
     // bf16 mode: whoever writes this layer's state LAST (dropout, else a separate activation pass, else the edge's own
     // kernel) also writes the bf16 copy the next conv edge multiplies with
     const bool want = bf16 && i < edges_.size() && edges_[i]->WantsBf16Input();
-    const bool drop = train && l->HasDropout(), act_pass = l->HasSeparateActivationPass();
+    const bool act_pass = l->HasSeparateActivationPass();
+    // dropout inside the edge's epilogue (no mask tensor) when the backward pass will not need the mask either
+    static const bool no_fuse_drop = getenv("CONVNET_B200_NO_FUSED_DROPOUT") && getenv("CONVNET_B200_NO_FUSED_DROPOUT")[0] == '1';
+    const bool fuse_drop = train && l->HasDropout() && !no_fuse_drop && !act_pass && e->CanFuseDropout() && DropoutFolds(i);
+    if (fuse_drop) e->SetDropoutRequest(l->DropoutProb(), l->DropoutScale(), l->DropoutSeed(step_, dropout_salt_));
+    const bool drop = train && l->HasDropout() && !fuse_drop;
     e->SetEmitUp(want && !drop && !act_pass);
     e->ComputeUp(layers_[i - 1]->GetState(), l->GetState(), /*overwrite=*/true, train);
     l->ApplyActivation(want && !drop && act_pass);
-    l->ApplyDropout(train, step_, dropout_salt_, want && drop);
+    if (!fuse_drop) l->ApplyDropout(train, step_, dropout_salt_, want && drop);
   }
+}
+
+bool ConvNet::DropoutFolds(size_t i) const {
+  static const bool no_fold = getenv("CONVNET_B200_NO_DROPOUT_FOLD") && getenv("CONVNET_B200_NO_DROPOUT_FOLD")[0] == '1';
+  if (no_fold || i == 0 || i >= edges_.size()) return false;        // edges_[i]: the edge whose ComputeDown writes layers_[i]'s derivative
+  const Layer* l = layers_[i];
+  return l->HasDropout() && l->GetActivation() == RECTIFIED_LINEAR && !l->HasSeparateDerivPass() && edges_[i]->CanScaleDeriv();
 }
 
 void ConvNet::ComputeDeriv() { OutputLayer().ComputeDeriv(); }
@@ -346,9 +373,7 @@ void ConvNet::Bprop() {                                      // convnet.cc:390-4
     if (!in->IsInput()) {
       const bool want_in = bf16 && i >= 2 && edges_[i - 2]->WantsBf16Deriv();
       // dropout derivative of a ReLU layer = one factor on the kept units, which the fused mask already selects
-      static const bool no_fold = getenv("CONVNET_B200_NO_DROPOUT_FOLD") && getenv("CONVNET_B200_NO_DROPOUT_FOLD")[0] == '1';
-      const bool fold = !no_fold && dropout_active_ && in->HasDropout() && in->GetActivation() == RECTIFIED_LINEAR &&
-                        !in->HasSeparateDerivPass() && e->CanScaleDeriv();
+      const bool fold = dropout_active_ && in->HasDropout() && DropoutFolds((size_t)i - 1);
       if (fold) { e->SetDerivScale(in->DropoutScale()); in->SetDropoutDerivFolded(true); }
       const bool drop_pass = in->HasDropout() && !fold;
       e->SetEmitDown(want_in && !drop_pass && !in->HasSeparateDerivPass());
@@ -387,6 +412,11 @@ void ConvNet::IssueBucketUpdate(const Bucket& b) {
   void* main_stream = convnet_b200_get_stream();
   convnet_b200_set_stream(opt_);
   cnb_sgd_momentum_multi(tensors.data(), (int)tensors.size());
+  // what the next step's dgrad derives from these weights alone (bf16 filter banks): rebuilt here, behind the update
+  static const bool no_prestage = getenv("CONVNET_B200_NO_PRESTAGE") && getenv("CONVNET_B200_NO_PRESTAGE")[0] == '1';
+  if (!no_prestage)
+    for (int i = b.trigger; i <= b.last; i++)
+      if (EdgeWithWeight* w = dynamic_cast<EdgeWithWeight*>(edges_[i])) w->PrestageDown();
   convnet_b200_set_stream(main_stream);
   opt_pending_ = true;
 }

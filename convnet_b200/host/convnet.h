@@ -45,6 +45,8 @@ class Layer {                                   // src/layer.{h,cc}, reduced to 
   void ApplyDerivativeofDropout(bool emit_bf16 = false);
   bool HasDropout() const { return config_.dropprob > 0 && !config_.is_input; }
   float DropoutScale() const { return 1.0f / (1.0f - config_.dropprob); }
+  float DropoutProb() const { return config_.dropprob; }
+  unsigned long long DropoutSeed(unsigned long long step, unsigned long long salt) const;
   void SetDropoutDerivFolded(bool v) { dropout_deriv_folded_ = v; }   // this step: the edge above scaled the derivative instead
   bool HasSeparateActivationPass() const { return config_.activation == RECTIFIED_LINEAR && !activation_fused_; }
   bool HasSeparateDerivPass() const { return config_.activation == RECTIFIED_LINEAR && !deriv_fused_; }
@@ -150,6 +152,9 @@ class ConvNet {
   // enqueued on side_, and once the bucket's edges have finished their dgrad the multi-tensor SGD step of that bucket
   // follows on the same stream — the exchange and the update of the FC layers hide under the conv back-propagation.
   void IssueBucketUpdate(const Bucket& b);
+  // layers_[i] is a ReLU layer with dropout whose derivative is written by a dgrad that can apply relu'(state) * 1/(1-p)
+  // itself: the backward pass needs no mask tensor, and the forward pass may fuse the dropout into the edge below
+  bool DropoutFolds(size_t i) const;
   void WaitSide();
   DataParallelSync* dp_ = nullptr;
   std::vector<Bucket> buckets_;

@@ -198,6 +198,7 @@ void ConvEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool tra
   if (emit_up_ && !bias_pass) convnet_b200_emit_bf16_next();
   if (image_size_t_ == 1) {
     if (fused) convnet_b200_fuse_next(bias_.GetDevData(), 1, nullptr);
+    ApplyDropoutRequest(fused);
     Matrix::ConvUp(input, weights_, output, conv_desc_, scale_targets);
   } else {
     Matrix::Conv3DUp(input, weights_, output, conv_desc_, scale_targets);
@@ -233,6 +234,12 @@ void ConvEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, 
   if (image_size_t_ == 1) Matrix::ConvDown(deriv_output, weights_, deriv_input, conv_desc_, scale_targets);
   else Matrix::Conv3DDown(deriv_output, weights_, deriv_input, conv_desc_, scale_targets);
   NoteDown();
+  if (image_size_t_ == 1) RememberDown(deriv_output, deriv_input);
+}
+void ConvEdge::PrestageDown() {
+  if (!down_out_ || !down_in_ || image_size_t_ != 1) return;
+  convnet_b200_prestage_next();
+  Matrix::ConvDown(*down_out_, weights_, *down_in_, conv_desc_, 0);
 }
 
 void ConvEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {   // :183-245
@@ -318,6 +325,7 @@ void FCEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train
   if (fused) convnet_b200_fuse_next(bias_.GetDevData(), 1, nullptr);
   const bool bias_pass = !has_no_bias_ && !fused;
   if (emit_up_ && !bias_pass) convnet_b200_emit_bf16_next();
+  ApplyDropoutRequest(fused);
   Matrix::ConvUp(input, weights_, output, desc_, overwrite ? 0 : 1);     // output = input * W^T
   NoteUp();
   if (bias_pass) { if (emit_up_) convnet_b200_emit_bf16_next(); output.AddRowVec(bias_); }
@@ -377,6 +385,7 @@ void ConvOneToOneEdge::ComputeUp(Matrix& input, Matrix& output, bool overwrite, 
   if (fused) convnet_b200_fuse_next(bias_.GetDevData(), 1, nullptr);
   const bool bias_pass = !has_no_bias_ && !fused;
   if (emit_up_ && !bias_pass) convnet_b200_emit_bf16_next();
+  ApplyDropoutRequest(fused);
   Matrix::ConvUp(input, weights_, output, desc_, overwrite ? 0 : 1);
   NoteUp();
   if (!has_no_bias_ && !fused) {
@@ -394,6 +403,12 @@ void ConvOneToOneEdge::ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& 
   ApplyBiasGradRequest();
   Matrix::ConvDown(deriv_output, weights_, deriv_input, desc_, overwrite ? 0 : 1);
   NoteDown();
+  RememberDown(deriv_output, deriv_input);
+}
+void ConvOneToOneEdge::PrestageDown() {
+  if (!down_out_ || !down_in_) return;
+  convnet_b200_prestage_next();
+  Matrix::ConvDown(*down_out_, weights_, *down_in_, desc_, 0);
 }
 void ConvOneToOneEdge::ComputeOuter(Matrix& input, Matrix& deriv_output) {                        // :87-102
   const int batch_size = input.GetRows();

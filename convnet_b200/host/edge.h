@@ -105,6 +105,11 @@ class Edge {
   // into the dgrad epilogue (convnet_b200_fuse_next_scale); only edges whose ComputeDown is a conv dgrad with the mask fused
   void SetDerivScale(float s) { deriv_scale_ = s; }
   virtual bool CanScaleDeriv() const { return false; }
+  // The dropout of the destination layer rides in ComputeUp's conv epilogue behind the fused bias + ReLU
+  // (convnet_b200_fuse_next_dropout: no mask tensor — ConvNet asks only when the backward pass folds the dropout derivative
+  // into the dgrad above, see ConvNet::DropoutFolds).  One-shot: the next ComputeUp consumes it.
+  virtual bool CanFuseDropout() const { return false; }
+  void SetDropoutRequest(float prob, float scale, unsigned long long seed) { drop_prob_ = prob; drop_scale_ = scale; drop_seed_ = seed; }
   virtual bool CanProduceBiasGrad() const { return false; }   // ComputeDown kernels that take the request
   virtual bool WantsBf16Input() const { return false; }      // this edge reads its input (fprop / wgrad) as bf16
   virtual bool WantsBf16Deriv() const { return false; }      // this edge reads its output derivative (wgrad / dgrad) as bf16
@@ -121,6 +126,12 @@ class Edge {
   bool emit_up_ = false, emit_down_ = false;
   BiasGradTarget bg_request_;
   float deriv_scale_ = 1.f;
+  float drop_prob_ = 0.f, drop_scale_ = 0.f;
+  unsigned long long drop_seed_ = 0;
+  void ApplyDropoutRequest(bool fused_epilogue) {   // call right before the ComputeUp kernel (after convnet_b200_fuse_next)
+    if (drop_scale_ != 0.f && fused_epilogue) convnet_b200_fuse_next_dropout(drop_prob_, drop_scale_, drop_seed_);
+    drop_scale_ = 0.f;
+  }
   void ApplyBiasGradRequest() {            // call right before the ComputeDown kernel
     if (bg_request_.grad_bias) convnet_b200_fuse_next_bias_grad(bg_request_.grad_bias, bg_request_.st, bg_request_.so);
     bg_request_ = BiasGradTarget();
@@ -137,6 +148,9 @@ struct SideLane { cudaStream_t stream = nullptr; cudaEvent_t ready = nullptr; bo
 class EdgeWithWeight : public Edge {
  public:
   void SetSideLane(SideLane* s) { side_ = s; }
+  // after this edge's optimizer step, on the optimizer's stream: rebuild what the next ComputeDown derives from the
+  // weights alone (convnet_b200_prestage_next), off the next step's critical path.  Default: nothing to prepare.
+  virtual void PrestageDown() {}
   explicit EdgeWithWeight(const EdgeConfig& c) : Edge(c), has_no_bias_(c.has_no_bias), scale_gradients_(c.scale_gradients), num_grads_received_(0) {}
   bool HasNoParameters() const override { return false; }
   void UpdateWeights() override;                                         // src/edge_with_weight.cc:96-118
@@ -177,6 +191,13 @@ class EdgeWithWeight : public Edge {
   float scale_gradients_;
   int num_grads_received_;
   int bf_up_ = -1, bf_down_ = -1, bf_outer_ = -1;        // -1 unknown, 0 tf32 / fp32 path, 1 bf16 path
+  // the tensors of the last ComputeDown that took the bf16 path (layer-owned, stable): PrestageDown re-describes that call
+  Matrix* down_out_ = nullptr;
+  Matrix* down_in_ = nullptr;
+  void RememberDown(Matrix& deriv_output, Matrix& deriv_input) {
+    down_out_ = bf_down_ == 1 ? &deriv_output : nullptr;
+    down_in_ = bf_down_ == 1 ? &deriv_input : nullptr;
+  }
   bool bias_grad_fused_ = false;                         // this step's bias gradient comes from the edge above (ComputeOuter skips SumRows)
 };
 
@@ -189,11 +210,13 @@ class ConvEdge : public EdgeWithWeight {
   void SetGradMemory(Matrix& p) override;
   void ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) override;
   void ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) override;
+  void PrestageDown() override;
   void ComputeOuter(Matrix& input, Matrix& deriv_output) override;
   double FlopsUp() const override;
   int FanIn() const override;
   ConvDesc GetConvDesc() const { return conv_desc_; }
   bool CanFuseReLU() const override { return !has_no_bias_ && shared_bias_ && image_size_t_ == 1; }
+  bool CanFuseDropout() const override { return fuse_relu_ && CanFuseReLU(); }
   bool CanFuseMask() const override { return image_size_t_ == 1; }
   bool BiasIsPerChannel2D() const override { return !has_no_bias_ && shared_bias_ && image_size_t_ == 1; }
 
@@ -216,6 +239,7 @@ class FCEdge : public EdgeWithWeight {          // weights [Cout x K] column-maj
   double FlopsUp() const override;
   int FanIn() const override { return num_inputs_; }
   bool CanFuseReLU() const override { return !has_no_bias_; }
+  bool CanFuseDropout() const override { return fuse_relu_ && CanFuseReLU(); }
   bool CanFuseMask() const override { return true; }
 
 
@@ -234,10 +258,12 @@ class ConvOneToOneEdge : public EdgeWithWeight {
   void SetGradMemory(Matrix& p) override;
   void ComputeUp(Matrix& input, Matrix& output, bool overwrite, bool train) override;
   void ComputeDown(Matrix& deriv_output, Matrix& input, Matrix& output, Matrix& deriv_input, bool overwrite) override;
+  void PrestageDown() override;
   void ComputeOuter(Matrix& input, Matrix& deriv_output) override;
   double FlopsUp() const override;
   int FanIn() const override { return num_input_channels_; }
   bool CanFuseReLU() const override { return !has_no_bias_; }
+  bool CanFuseDropout() const override { return fuse_relu_ && CanFuseReLU(); }
   bool CanFuseMask() const override { return true; }
 
  private:

@@ -78,6 +78,8 @@ SIGNATURES = {
     "convnet_b200_emit_bf16_next": [],
     "convnet_b200_reserve_sms": [I],
     "convnet_b200_pool_cache_next": [],
+    "convnet_b200_prestage_next": [],
+    "convnet_b200_fuse_next_dropout": [ct.c_float, ct.c_float, ct.c_ulonglong],
     "convnet_b200_fuse_next_scale": [F],
     "convnet_b200_fuse_next_bias_grad": [FP, F, F],
     "convnet_b200_bf16_invalidate": [FP],

@@ -64,6 +64,21 @@ void convnet_b200_fuse_next_scale(float scale);
  * not use this request (or must call convnet_b200_bf16_invalidate(NULL)).  2-D windows up to 3 x 3. */
 void convnet_b200_pool_cache_next(void);
 
+/* One-shot request for the next convUp* call (after its bias / ReLU, if those are requested too): dropout of the result with
+ * the generator of cnb_dropout — element i of the target is kept iff hash(seed + i) >= dropprob, kept values are multiplied
+ * by `scale` — exactly as if cnb_dropout(target, mask, n, dropprob, scale, seed) followed the call, except that NO mask
+ * tensor is written: the caller's backward pass must not need one (for a ReLU layer the kept units are the non-zero ones:
+ * convnet_b200_fuse_next_scale on the dgrad that produces this layer's derivative).  The bf16 lean kernels apply it in
+ * the epilogue; every other path runs one trailing pass inside the call. */
+void convnet_b200_fuse_next_dropout(float dropprob, float scale, unsigned long long seed);
+
+/* One-shot request for the next convDown* call: do not compute anything, only prepare on the current stream what that call
+ * derives from the FILTERS alone — in bf16 mode the per-stride-phase, tap-flipped bf16 filter banks the dgrad kernels read
+ * (DESIGN.md §3).  The derivative and target tensors are not touched (their shapes must still describe the call).  A
+ * trainer issues this right after the optimizer step of a layer, on the optimizer's stream, so that the next step's
+ * convDown finds the banks ready instead of rebuilding them on the critical path. */
+void convnet_b200_prestage_next(void);
+
 /* The conv kernels are persistent: one CTA (or CTA pair) per SM, each owning most of the SM's shared memory.  A kernel
  * of another library that must run CONCURRENTLY (an NCCL collective on a side stream) cannot co-reside with them and
  * would otherwise wait for — or push out — a whole wave.  convnet_b200_reserve_sms(n) makes the persistent grids leave

@@ -2,6 +2,8 @@
 re-converts the fp32 source and aborts on a mismatch.
   mode "train": training steps of a net in bf16 mode — every bf16 copy written by a producing kernel (conv / pool-undo /
                 rnorm epilogues, dropout, SGD) must be bit-identical to a conversion of the fp32 tensor it shadows;
+  mode "params": (no verify mode needed) training steps with fixed seeds, then a checksum of the parameter bits — the test
+                compares runs whose environment switches fusions on and off;
   mode "stale": stage a tensor, overwrite it behind the library's back, use it — the library must notice and abort."""
 import os
 import sys
@@ -17,8 +19,8 @@ from convnet_b200.abi import GetConvDesc  # noqa: E402
 from convnet_b200.matrix import CUDAMatrix  # noqa: E402
 from convnet_b200.net import Net  # noqa: E402
 
-assert os.environ.get("CONVNET_B200_STAGE_VERIFY") == "1"
 mode = sys.argv[1]
+assert mode == "params" or os.environ.get("CONVNET_B200_STAGE_VERIFY") == "1"
 L = lib.load()
 lib.set_precision("bf16")
 if mode == "train":
@@ -33,6 +35,16 @@ if mode == "train":
     torch.cuda.synchronize()
     n.close()
     print("VERIFY-TRAIN-OK")
+elif mode == "params":
+    model, batch, steps = sys.argv[2], int(sys.argv[3]), int(sys.argv[4])
+    torch.manual_seed(7)
+    n = Net(model, batch, seed=3)
+    n.input_tensor().normal_()
+    n.labels_tensor().copy_(torch.randint(0, n.num_classes, (batch,), device="cuda", dtype=torch.int32))
+    losses = [n.train_step(True) for _ in range(steps)]
+    bits = n.params_tensor().view(torch.int32).to(torch.int64)
+    print("PARAMS", int((bits * (torch.arange(bits.numel(), device="cuda") % 8191 + 1)).sum().item()), " ".join("%.9g" % v for v in losses))
+    n.close()
 elif mode == "stale":
     N, W, Cin, Cout = 128, 8, 64, 64
     d = GetConvDesc(Cin, Cout, 3, 3, 1, 1, 1, 1)

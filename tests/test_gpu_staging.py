@@ -11,16 +11,33 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.gpu
 
 
-def _run(*args):
-    env = dict(os.environ, CONVNET_B200_STAGE_VERIFY="1")
+def _run(*args, **extra_env):
+    env = dict(os.environ, CONVNET_B200_STAGE_VERIFY="1", **extra_env)
     return subprocess.run([sys.executable, os.path.join(ROOT, "tests", "staging_worker.py"), *args],
                           capture_output=True, text=True, timeout=900, env=env)
 
 
-@pytest.mark.parametrize("model,batch,steps", [("tiny", 32, 3), ("alexnet", 32, 2)])
+@pytest.mark.parametrize("model,batch,steps", [("tiny", 32, 3), ("alexnet", 32, 2), ("alexnet", 128, 2)])
 def test_emitted_copies_equal_a_fresh_conversion(model, batch, steps):
     r = _run("train", model, str(batch), str(steps))
     assert r.returncode == 0 and "VERIFY-TRAIN-OK" in r.stdout, (r.returncode, r.stdout[-1500:], r.stderr[-1500:])
+
+
+def test_fused_dropout_and_prestaged_banks_do_not_change_the_training_step():
+    """AlexNet, batch 128, bf16: the step with dropout fused into the 1x1 / fc epilogues (no mask tensor), its derivative
+    folded into the dgrad above, and the dgrad filter banks rebuilt behind the optimizer step, leaves bit-identical
+    parameters and losses to the step with separate dropout / mask passes and banks built on first use."""
+    def run(**env):
+        e = dict(os.environ, **env)
+        e.pop("CONVNET_B200_STAGE_VERIFY", None)
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "staging_worker.py"), "params", "alexnet", "128", "3"],
+                           capture_output=True, text=True, timeout=900, env=e)
+        lines = [ln for ln in r.stdout.splitlines() if ln.startswith("PARAMS")]
+        assert r.returncode == 0 and lines, (r.returncode, r.stdout[-1000:], r.stderr[-1500:])
+        return lines[-1]
+    fused = run()
+    plain = run(CONVNET_B200_NO_FUSED_DROPOUT="1", CONVNET_B200_NO_DROPOUT_FOLD="1", CONVNET_B200_NO_PRESTAGE="1")
+    assert fused == plain
 
 
 def test_stale_copy_is_detected_in_verify_mode():
@@ -127,3 +144,99 @@ def test_max_pool_undo_from_tie_masks_is_bit_identical(shape, pad):
         assert torch.equal(out.storage, ref.storage)
     finally:
         L.convnet_b200_bf16_invalidate(None)
+
+
+@pytest.mark.parametrize("precision", ["bf16", "fp32"])
+@pytest.mark.parametrize("k,pad", [(1, 0), (3, 1)])
+def test_fused_dropout_equals_the_separate_pass(precision, k, pad):
+    """convnet_b200_fuse_next_dropout: bias + ReLU + dropout in the conv call == the same call followed by cnb_dropout with
+    the same seed, bit for bit — in the lean bf16 kernel's epilogue and on the trailing-pass fallback (fp32) — and the
+    bf16 twin requested with it holds the values AFTER the dropout."""
+    import torch
+    from convnet_b200 import conv_gemm as cg
+    from convnet_b200 import lib
+    from convnet_b200.abi import GetConvDesc
+    from convnet_b200.matrix import CUDAMatrix
+    L = lib.load()
+    lib.set_precision(precision)
+    try:
+        N, W, Cin, Cout = 128, 14, 64, 128
+        d = GetConvDesc(Cin, Cout, k, k, 1, 1, pad, pad)
+        g = torch.Generator(device="cuda").manual_seed(11)
+        x = CUDAMatrix(N, W * W * Cin, (N, W, W, Cin)); x.storage.normal_(generator=g)
+        w = CUDAMatrix(Cout, k * k * Cin, (Cout, k, k, Cin)); w.storage.normal_(generator=g).mul_(0.05)
+        b = torch.randn(Cout, device="cuda", generator=g)
+        n_out = N * W * W * Cout
+        seed, prob = 0x1234567890ABCDEF, 0.3
+        scale = 1.0 / (1.0 - prob)
+        # reference: conv (+bias, ReLU) then the stand-alone dropout pass
+        ref = CUDAMatrix(N, W * W * Cout, (N, W, W, Cout)); mask = torch.empty(n_out, device="cuda")
+        L.convnet_b200_fuse_next(b.data_ptr(), 1, None); cg.convUp(x, w, ref, d)
+        L.cnb_dropout(ref.ptr, mask.data_ptr(), n_out, prob, scale, seed)
+        # fused
+        out = CUDAMatrix(N, W * W * Cout, (N, W, W, Cout))
+        if precision == "bf16":                                   # operands staged: the call is the conv kernel alone
+            L.convnet_b200_bf16_stage(x.ptr, x.storage.numel()); L.convnet_b200_bf16_stage(w.ptr, w.storage.numel())
+        L.convnet_b200_reset_launch_count()
+        L.convnet_b200_fuse_next(b.data_ptr(), 1, None); L.convnet_b200_fuse_next_dropout(prob, scale, seed)
+        L.convnet_b200_emit_bf16_next(); cg.convUp(x, w, out, d)
+        if precision == "bf16":
+            assert lib.last_conv_path() == "tcgen05-bf16"
+            assert L.convnet_b200_launch_count() == 1             # bias, ReLU, dropout and the bf16 twin all in its epilogue
+        assert torch.equal(out.storage, ref.storage)
+        kept = (out.storage != 0).float().mean().item()
+        assert 0.2 < kept < 0.5                                   # ~ half pass the ReLU, 70 % of those are kept
+        if precision == "bf16":                                   # the twin the next edge would read == a conversion of the result
+            assert L.convnet_b200_bf16_is_staged(out.ptr, n_out) == 1
+            w2 = CUDAMatrix(Cout, Cout, (Cout, 1, 1, Cout)); w2.storage.normal_(generator=g).mul_(0.05)
+            d2 = GetConvDesc(Cout, Cout, 1, 1, 1, 1, 0, 0)
+            z1 = CUDAMatrix(N, W * W * Cout, (N, W, W, Cout)); cg.convUp(out, w2, z1, d2)
+            L.convnet_b200_bf16_invalidate(out.ptr)
+            z2 = CUDAMatrix(N, W * W * Cout, (N, W, W, Cout)); cg.convUp(out, w2, z2, d2)
+            assert torch.equal(z1.storage, z2.storage)
+        # the request is one-shot
+        out2 = CUDAMatrix(N, W * W * Cout, (N, W, W, Cout))
+        L.convnet_b200_fuse_next(b.data_ptr(), 1, None); cg.convUp(x, w, out2, d)
+        assert (out2.storage != 0).float().mean().item() > kept + 0.1
+    finally:
+        L.convnet_b200_bf16_invalidate(None)
+        lib.set_precision("fp32")
+
+
+def test_prestaged_dgrad_banks_are_used_and_dropped_on_weight_writes():
+    """convnet_b200_prestage_next: the convDown that follows builds nothing and returns the same derivative; touching the
+    weights through the library drops the banks again."""
+    import torch
+    from convnet_b200 import conv_gemm as cg
+    from convnet_b200 import lib
+    from convnet_b200.abi import GetConvDesc, num_modules
+    from convnet_b200.matrix import CUDAMatrix
+    L = lib.load()
+    lib.set_precision("bf16")
+    try:
+        N, W, Cin, Cout, k, s, pad = 128, 27, 64, 96, 5, 2, 1
+        mod = num_modules(W, k, s, pad)
+        d = GetConvDesc(Cin, Cout, k, k, s, s, pad, pad)
+        g = torch.Generator(device="cuda").manual_seed(5)
+        w = CUDAMatrix(Cout, k * k * Cin, (Cout, k, k, Cin)); w.storage.normal_(generator=g).mul_(0.05)
+        dy = CUDAMatrix(N, mod * mod * Cout, (N, mod, mod, Cout)); dy.storage.normal_(generator=g)
+        dx0 = CUDAMatrix(N, W * W * Cin, (N, W, W, Cin)); dx1 = CUDAMatrix(N, W * W * Cin, (N, W, W, Cin))
+        dx1.storage.fill_(7.0)
+        cg.convDown(dy, w, dx0, d)                                 # builds the banks on first use
+        assert lib.last_conv_path() == "tcgen05-bf16"
+        L.convnet_b200_bf16_invalidate(None)
+        L.convnet_b200_reset_launch_count()
+        L.convnet_b200_prestage_next(); cg.convDown(dy, w, dx1, d)
+        assert L.convnet_b200_launch_count() == 1                  # the bank kernel only
+        assert torch.all(dx1.storage == 7.0)                       # the target was not touched
+        L.convnet_b200_reset_launch_count()
+        cg.convDown(dy, w, dx1, d)
+        with_banks = L.convnet_b200_launch_count()
+        assert torch.equal(dx1.storage, dx0.storage)
+        L.cnb_relu(w.ptr, w.storage.numel())                       # a library write to the weights: banks stale
+        L.convnet_b200_reset_launch_count()
+        cg.convDown(dy, w, dx1, d)
+        assert L.convnet_b200_launch_count() == with_banks + 1     # rebuilt
+    finally:
+        L.convnet_b200_bf16_invalidate(None)
+        lib.set_precision("fp32")
