@@ -46,6 +46,11 @@ namespace cnb {
   abort();
 }
 
+// programmatic dependent launch: this CTA does not mind the NEXT kernel of the stream being placed on the machine already
+// (only kernels launched with the PDL attribute use it, and those wait for this grid's completion before their first
+// global access — conv_tc.cu: launch_fast); a no-op for every other successor
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // the dropout generator: a counter-based hash (splitmix64 finaliser) of seed + element index, top 32 bits -> [0, 1)
 __host__ __device__ __forceinline__ uint32_t hash_u32(unsigned long long x) {
   x += 0x9E3779B97F4A7C15ULL; x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ULL; x = (x ^ (x >> 27)) * 0x94D049BB133111EBULL;

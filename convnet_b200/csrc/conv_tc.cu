@@ -237,6 +237,7 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   ptx::tc_fence_before();
   if constexpr (cta2) ptx::cluster_sync(); else __syncthreads();              // peer barriers are initialised before anyone signals them
   ptx::tc_fence_after();
+  ptx::pdl_launch_dependents();       // a lean kernel queued behind this one may start its prologue (it waits for this grid's end)
   const int t_first = cta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int t_step = cta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t tmem_base = ctl->tmem_base;
@@ -681,6 +682,10 @@ tc_fast_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   ptx::tc_fence_before();
   if constexpr (PAIR) ptx::cluster_sync(); else __syncthreads();
   ptx::tc_fence_after();
+  // everything above touched only shared memory, TMEM and the kernel parameters: with programmatic dependent launch it has
+  // overlapped the tail of the previous kernel in the stream; from here on this kernel reads what that kernel wrote
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int t_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int t_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t tmem_base = ctl->tmem_base;
@@ -1210,22 +1215,29 @@ void launch_fast(const CUtensorMap& a, const CUtensorMap& b, TcParams& p) {
       CNB_CUDA_CHECK(cudaFuncSetAttribute(tc_fast_kernel<OP, !XM, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if (dev < 64) attr_devices |= 1ULL << dev;
   }
+  // programmatic dependent launch: the kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) may run while
+  // the previous kernel of the stream drains; it waits (griddepcontrol.wait) before its first global access
+  static const bool pdl = !(getenv("CONVNET_B200_NO_PDL") && getenv("CONVNET_B200_NO_PDL")[0] == '1');
+  cudaLaunchConfig_t cfg = {};
+  cfg.blockDim = dim3(kFastThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = state().stream;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (pdl) { attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[na].val.programmaticStreamSerializationAllowed = 1; na++; }
   if (p.cta2) {
     if constexpr (!XM) {
-      cudaLaunchConfig_t cfg = {};
       cfg.gridDim = dim3(2u * (unsigned)std::min(p.num_tiles, num_sms() / 2));
-      cfg.blockDim = dim3(kFastThreads);
-      cfg.dynamicSmemBytes = smem;
-      cfg.stream = state().stream;
-      cudaLaunchAttribute attr[1];
-      attr[0].id = cudaLaunchAttributeClusterDimension;
-      attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-      cfg.attrs = attr; cfg.numAttrs = 1;
+      attr[na].id = cudaLaunchAttributeClusterDimension;
+      attr[na].val.clusterDim.x = 2; attr[na].val.clusterDim.y = 1; attr[na].val.clusterDim.z = 1;
+      na++;
+      cfg.attrs = attr; cfg.numAttrs = na;
       CNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_fast_kernel<OP, !XM, false>, a, b, p));
     }
   } else {
-    const int grid = std::min(p.num_tiles, num_sms());
-    tc_fast_kernel<OP, false, XM><<<grid, kFastThreads, smem, state().stream>>>(a, b, p);
+    cfg.gridDim = dim3((unsigned)std::min(p.num_tiles, num_sms()));
+    cfg.attrs = attr; cfg.numAttrs = na;
+    CNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_fast_kernel<OP, false, XM>, a, b, p));
   }
   count_launch();
   CNB_LAUNCH_CHECK("tc_fast");
@@ -1301,6 +1313,7 @@ __global__ void __launch_bounds__(256) reduce_split_kernel(const float4* __restr
                                                            long long stride4, int splits, float st, float so,
                                                            const float* __restrict__ bias, long long per_channel4, int relu,
                                                            const float4* __restrict__ mask) {
+  pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < elems4; i += (long long)gridDim.x * blockDim.x) {
     float4 s = part[i];
     for (int k = 1; k < splits; k++) {

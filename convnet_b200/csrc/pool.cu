@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(256) pool_fwd_rows_kernel(PoolGeom g, const fl
                                                              float* __restrict__ targets, float so, int nv_shift,
                                                              __nv_bfloat16* __restrict__ targets16,
                                                              uint16_t* __restrict__ tie_masks) {
+  pdl_trigger();
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * g.modX;
   const int sx = S > 0 ? S : g.sx, sy = S > 0 ? S : g.sy;
@@ -282,6 +283,7 @@ __global__ void __launch_bounds__(256) pool_undo_rows_kernel(PoolGeom g, const f
                                                               float st, float so, const float* __restrict__ relu_mask,
                                                               int nv_shift, __nv_bfloat16* __restrict__ targets16,
                                                               float* __restrict__ rowsum) {
+  pdl_trigger();
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * g.W;
   const long long in_plane = (long long)g.N * g.W * g.H * blockIdx.y, out_plane = (long long)g.N * g.modX * g.modY * blockIdx.y;
@@ -380,6 +382,7 @@ __global__ void __launch_bounds__(256) pool_undo_masked_kernel(PoolGeom g, const
                                                                const uint16_t* __restrict__ tie_masks, float* targets,
                                                                float st, float so, int positive_only, int nv_shift,
                                                                __nv_bfloat16* __restrict__ targets16, float* __restrict__ rowsum) {
+  pdl_trigger();
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * g.W;
   const long long in_plane = (long long)g.N * g.W * g.H * blockIdx.y, out_plane = (long long)g.N * g.modX * g.modY * blockIdx.y;
@@ -465,6 +468,7 @@ __global__ void __launch_bounds__(256) pool_undo_masked_patch_kernel(PoolGeom g,
                                                                      float st, float so, int positive_only, int nv_shift,
                                                                      __nv_bfloat16* __restrict__ targets16,
                                                                      float* __restrict__ rowsum, int PX, int PY) {
+  pdl_trigger();
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * PX;
   const long long in_plane = (long long)g.N * g.W * g.H * blockIdx.y, out_plane = (long long)g.N * g.modX * g.modY * blockIdx.y;
@@ -557,6 +561,7 @@ __global__ void __launch_bounds__(256) pool_undo_patch_kernel(PoolGeom g, const 
                                                               const float* __restrict__ relu_mask, int nv_shift,
                                                               __nv_bfloat16* __restrict__ targets16,
                                                               float* __restrict__ rowsum, int PX, int PY) {
+  pdl_trigger();
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * PX;
   const long long in_plane = (long long)g.N * g.W * g.H * blockIdx.y, out_plane = (long long)g.N * g.modX * g.modY * blockIdx.y;

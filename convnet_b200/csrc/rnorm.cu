@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_fwd_tile_kernel(const float*
                                                                      __nv_bfloat16* __restrict__ y16, long long L, int F,
                                                                      int k, float alpha, float beta, int blocked, int relu,
                                                                      int vec) {
+  pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   float* X = sm;                               // [F][TL]
   float* Q = X + (size_t)F * TL;               // [F+1][TL] exclusive prefix of x^2
@@ -341,6 +342,7 @@ template <int TL>
 __global__ void __launch_bounds__(RN_THREADS) rnorm_undo_tile_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                       float* __restrict__ dx, long long L, int F, int k,
                                                                       float alpha, float beta, int blocked, int vec) {
+  pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   float* X = sm;                               // [F][TL]
   float* G = X + (size_t)F * TL;               // [F][TL]   dy, then p = dy * base^(-beta)

@@ -104,6 +104,13 @@ __device__ __forceinline__ void tma_load_5d(const void* desc, uint64_t* bar, voi
 __device__ __forceinline__ uint32_t cluster_ctarank() {
   uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r;
 }
+// Programmatic dependent launch (griddepcontrol): a kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// may become resident while its predecessor in the stream is still draining; pdl_wait() blocks until every prerequisite
+// grid has completed and its memory is visible.  pdl_launch_dependents() tells the scheduler this CTA no longer minds the
+// next kernel's CTAs being placed (they still wait at their own pdl_wait before touching global memory).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 __device__ __forceinline__ void cluster_sync() {       // all threads of all CTAs of the cluster
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
