@@ -50,6 +50,9 @@ namespace cnb {
 // (only kernels launched with the PDL attribute use it, and those wait for this grid's completion before their first
 // global access — conv_tc.cu: launch_fast); a no-op for every other successor
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+// ... and the other half: block until every kernel this one depends on has completed and its writes are visible.  First
+// statement of every kernel that launch_pdl() starts; a no-op when the launch carried no programmatic dependency.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 
 // the dropout generator: a counter-based hash (splitmix64 finaliser) of seed + element index, top 32 bits -> [0, 1)
 __host__ __device__ __forceinline__ uint32_t hash_u32(unsigned long long x) {
@@ -58,6 +61,23 @@ __host__ __device__ __forceinline__ uint32_t hash_u32(unsigned long long x) {
 }
 __host__ __device__ __forceinline__ float dropout_keep(unsigned long long x, float dropprob, float scale) {
   return hash_u32(x) * (1.0f / 4294967296.0f) >= dropprob ? scale : 0.f;
+}
+
+// launch with programmatic stream serialization allowed (CONVNET_B200_NO_PDL=1: plain launch).  ONLY for kernels that
+// execute pdl_wait() before their first global access.
+inline bool pdl_enabled() {
+  static const bool on = !(getenv("CONVNET_B200_NO_PDL") && getenv("CONVNET_B200_NO_PDL")[0] == '1');
+  return on;
+}
+template <typename... KArgs, typename... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  CNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...));
 }
 
 // ---- global state (one host thread per process/GPU, like the reference) -------------

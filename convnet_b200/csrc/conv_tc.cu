@@ -237,7 +237,8 @@ tc_conv_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__
   ptx::tc_fence_before();
   if constexpr (cta2) ptx::cluster_sync(); else __syncthreads();              // peer barriers are initialised before anyone signals them
   ptx::tc_fence_after();
-  ptx::pdl_launch_dependents();       // a lean kernel queued behind this one may start its prologue (it waits for this grid's end)
+  ptx::pdl_launch_dependents();       // the kernel queued behind this one may start its prologue (it waits for this grid's end)
+  ptx::pdl_wait();                    // ... as this one's just overlapped its predecessor's tail; from here on: global memory
   const int t_first = cta2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
   const int t_step = cta2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
   const uint32_t tmem_base = ctl->tmem_base;
@@ -1141,14 +1142,16 @@ void launch(const CUtensorMap& a, const CUtensorMap& b, TcParams& p) {
     cfg.blockDim = dim3(kThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = state().stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-    cfg.attrs = attr; cfg.numAttrs = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 2 : 1;
     CNB_CUDA_CHECK(cudaLaunchKernelEx(&cfg, tc_conv_kernel<OP, true>, a, b, p));
   } else {
     const int grid = std::min(p.num_tiles, num_sms());
-    tc_conv_kernel<OP, false><<<grid, kThreads, smem, state().stream>>>(a, b, p);
+    launch_pdl(tc_conv_kernel<OP, false>, dim3((unsigned)grid), dim3(kThreads), smem, state().stream, a, b, p);
   }
   count_launch();
   CNB_LAUNCH_CHECK("tc_conv");
@@ -1217,7 +1220,7 @@ void launch_fast(const CUtensorMap& a, const CUtensorMap& b, TcParams& p) {
   }
   // programmatic dependent launch: the kernel's prologue (barrier init, TMEM allocation, descriptor prefetch) may run while
   // the previous kernel of the stream drains; it waits (griddepcontrol.wait) before its first global access
-  static const bool pdl = !(getenv("CONVNET_B200_NO_PDL") && getenv("CONVNET_B200_NO_PDL")[0] == '1');
+  const bool pdl = pdl_enabled();
   cudaLaunchConfig_t cfg = {};
   cfg.blockDim = dim3(kFastThreads);
   cfg.dynamicSmemBytes = smem;
@@ -1313,6 +1316,7 @@ __global__ void __launch_bounds__(256) reduce_split_kernel(const float4* __restr
                                                            long long stride4, int splits, float st, float so,
                                                            const float* __restrict__ bias, long long per_channel4, int relu,
                                                            const float4* __restrict__ mask) {
+  pdl_wait();
   pdl_trigger();
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < elems4; i += (long long)gridDim.x * blockDim.x) {
     float4 s = part[i];
@@ -1338,8 +1342,8 @@ void reduce_split(const float* part, float* out, long long elems, int splits, fl
                   long long per_channel, int relu, const float* mask) {
   const long long e4 = elems / 4;
   const int grid = (int)std::min<long long>(std::max<long long>(ceil_div<long long>(e4, 256), 1), 8LL * num_sms());
-  reduce_split_kernel<<<grid, 256, 0, state().stream>>>((const float4*)part, (float4*)out, e4, e4, splits, st, so, bias,
-                                                        per_channel / 4, relu, (const float4*)mask);
+  launch_pdl(reduce_split_kernel, dim3((unsigned)grid), dim3(256), 0, state().stream, (const float4*)part, (float4*)out, e4, e4, splits,
+             st, so, bias, per_channel / 4, relu, (const float4*)mask);
   count_launch();
   CNB_LAUNCH_CHECK("reduce_split");
 }

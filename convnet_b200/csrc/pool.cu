@@ -215,6 +215,7 @@ __global__ void __launch_bounds__(256) pool_fwd_rows_kernel(PoolGeom g, const fl
                                                              float* __restrict__ targets, float so, int nv_shift,
                                                              __nv_bfloat16* __restrict__ targets16,
                                                              uint16_t* __restrict__ tie_masks) {
+  pdl_wait();
   pdl_trigger();
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * g.modX;
@@ -283,6 +284,7 @@ __global__ void __launch_bounds__(256) pool_undo_rows_kernel(PoolGeom g, const f
                                                               float st, float so, const float* __restrict__ relu_mask,
                                                               int nv_shift, __nv_bfloat16* __restrict__ targets16,
                                                               float* __restrict__ rowsum) {
+  pdl_wait();
   pdl_trigger();
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * g.W;
@@ -382,6 +384,7 @@ __global__ void __launch_bounds__(256) pool_undo_masked_kernel(PoolGeom g, const
                                                                const uint16_t* __restrict__ tie_masks, float* targets,
                                                                float st, float so, int positive_only, int nv_shift,
                                                                __nv_bfloat16* __restrict__ targets16, float* __restrict__ rowsum) {
+  pdl_wait();
   pdl_trigger();
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * g.W;
@@ -468,6 +471,7 @@ __global__ void __launch_bounds__(256) pool_undo_masked_patch_kernel(PoolGeom g,
                                                                      float st, float so, int positive_only, int nv_shift,
                                                                      __nv_bfloat16* __restrict__ targets16,
                                                                      float* __restrict__ rowsum, int PX, int PY) {
+  pdl_wait();
   pdl_trigger();
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * PX;
@@ -561,6 +565,7 @@ __global__ void __launch_bounds__(256) pool_undo_patch_kernel(PoolGeom g, const 
                                                               const float* __restrict__ relu_mask, int nv_shift,
                                                               __nv_bfloat16* __restrict__ targets16,
                                                               float* __restrict__ rowsum, int PX, int PY) {
+  pdl_wait();
   pdl_trigger();
   const unsigned NV = g.N / VEC;
   const unsigned rowlen = NV * PX;
@@ -681,7 +686,7 @@ static bool launch_fwd(const PoolGeom& g, const float* images, float* targets, f
     const dim3 rgrid((unsigned)g.modY, planes);
     const int sh = pow2_shift(g.N / VEC);
     const int S = (g.sx == g.sy && g.sx <= 2) ? g.sx : 0;
-#define CNB_POOL_FWD(KK, SS) pool_fwd_rows_kernel<VEC, MAX, KK, SS><<<rgrid, 256, 0, s>>>(g, images, targets, so, sh, t16, masks)
+#define CNB_POOL_FWD(KK, SS) launch_pdl(pool_fwd_rows_kernel<VEC, MAX, KK, SS>, rgrid, dim3(256), 0, s, g, images, targets, so, sh, t16, masks)
     if (k <= 2) { if (S == 1) CNB_POOL_FWD(2, 1); else if (S == 2) CNB_POOL_FWD(2, 2); else CNB_POOL_FWD(2, 0); }
     else { if (S == 1) CNB_POOL_FWD(3, 1); else if (S == 2) CNB_POOL_FWD(3, 2); else CNB_POOL_FWD(3, 0); }
 #undef CNB_POOL_FWD
@@ -744,8 +749,8 @@ static bool launch_undo(const PoolGeom& g, const float* images, const float* gra
           const int PX = (g.W - 1 - g.px) / 2 + 1, PY = (g.H - 1 - g.py) / 2 + 1;
           const int shp = pow2_shift(g.N / VEC);
           if (colsum && colsum_slices) *colsum_slices = PY;
-          pool_undo_masked_patch_kernel<VEC><<<dim3((unsigned)PY, planes), 256, 0, s>>>(g, grads, tm, targets, st, so, pos, shp, t16,
-                                                                                     colsum, PX, PY);
+          launch_pdl(pool_undo_masked_patch_kernel<VEC>, dim3((unsigned)PY, planes), dim3(256), 0, s, g, grads, tm, targets, st, so, pos,
+                     shp, t16, colsum, PX, PY);
           return t16 != nullptr;
         }
         if (colsum && colsum_slices) *colsum_slices = g.H;
@@ -759,8 +764,8 @@ static bool launch_undo(const PoolGeom& g, const float* images, const float* gra
         pool_patch_enabled()) {
       const int PX = (g.W - 1 - g.px) / 2 + 1, PY = (g.H - 1 - g.py) / 2 + 1;
       if (colsum && colsum_slices) *colsum_slices = PY;
-      pool_undo_patch_kernel<VEC><<<dim3((unsigned)PY, planes), 256, 0, s>>>(g, images, grads, acts, targets, st, so, mask, sh, t16,
-                                                                          colsum, PX, PY);
+      launch_pdl(pool_undo_patch_kernel<VEC>, dim3((unsigned)PY, planes), dim3(256), 0, s, g, images, grads, acts, targets, st, so, mask,
+                 sh, t16, colsum, PX, PY);
       return t16 != nullptr;
     }
     if (colsum && colsum_slices) *colsum_slices = g.H;

@@ -309,6 +309,7 @@ __global__ void __launch_bounds__(RN_THREADS) rnorm_fwd_tile_kernel(const float*
                                                                      __nv_bfloat16* __restrict__ y16, long long L, int F,
                                                                      int k, float alpha, float beta, int blocked, int relu,
                                                                      int vec) {
+  pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   float* X = sm;                               // [F][TL]
@@ -342,6 +343,7 @@ template <int TL>
 __global__ void __launch_bounds__(RN_THREADS) rnorm_undo_tile_kernel(const float* __restrict__ dy, const float* __restrict__ x,
                                                                       float* __restrict__ dx, long long L, int F, int k,
                                                                       float alpha, float beta, int blocked, int vec) {
+  pdl_wait();
   pdl_trigger();
   extern __shared__ __align__(16) float sm[];
   float* X = sm;                               // [F][TL]
@@ -447,8 +449,8 @@ static void launch_fwd_tile(const float* images, float* targets, __nv_bfloat16* 
     if (dev < 31) attr_dev_mask |= 1 << dev;
   }
   const long long tiles = ceil_div<long long>(L, TL);
-  rnorm_fwd_tile_kernel<TL><<<(unsigned)tiles, RN_THREADS, smem, state().stream>>>(images, targets, t16, L, F, k, alpha, beta,
-                                                                                  blocked ? 1 : 0, relu ? 1 : 0, vec ? 1 : 0);
+  launch_pdl(rnorm_fwd_tile_kernel<TL>, dim3((unsigned)tiles), dim3(RN_THREADS), smem, state().stream, images, targets, t16, L, F, k,
+             alpha, beta, blocked ? 1 : 0, relu ? 1 : 0, vec ? 1 : 0);
 }
 template <int TL>
 static void launch_undo_tile(const float* outGrads, const float* inputs, float* targets, long long L, int F, int k, float alpha,
@@ -460,8 +462,8 @@ static void launch_undo_tile(const float* outGrads, const float* inputs, float* 
     if (dev < 31) attr_dev_mask |= 1 << dev;
   }
   const long long tiles = ceil_div<long long>(L, TL);
-  rnorm_undo_tile_kernel<TL><<<(unsigned)tiles, RN_THREADS, smem, state().stream>>>(outGrads, inputs, targets, L, F, k, alpha,
-                                                                                   beta, blocked ? 1 : 0, vec ? 1 : 0);
+  launch_pdl(rnorm_undo_tile_kernel<TL>, dim3((unsigned)tiles), dim3(RN_THREADS), smem, state().stream, outGrads, inputs, targets, L,
+             F, k, alpha, beta, blocked ? 1 : 0, vec ? 1 : 0);
 }
 
 void rnorm_forward(const float* images, float* targets, long long L, int F, int k, float alpha, float beta,
