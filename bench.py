@@ -194,7 +194,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "tf32", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-prefetch", action="store_true", help="e2e: copy each batch synchronously instead of one step ahead")
-    ap.add_argument("--bucket-mb", type=float, default=8.0, help="gradient all-reduce bucket size")
+    ap.add_argument("--bucket-mb", type=float, default=128.0, help="gradient all-reduce bucket size")
     ap.add_argument("--no-cfg3", action="store_true", help="N > 1: skip the extra 256-images-per-GPU measurement")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -351,8 +351,10 @@ def main():
                        "arithmetic": "fp32 storage and master weights; conv/1x1/fc multiply in %s on tcgen05 with fp32 accumulate "
                                      "(conv1, Cin=3, always tf32); pool/rnorm/elementwise fp32" % args.precision,
                        "l2": "no flush needed: one step streams >3 GB of activations/weights through the 126 MB L2",
-                       "sync": ("NCCL all-reduce(avg) of the flat gradient buffer in %.0f MB buckets on a side stream, each followed by "
-                                "that bucket's SGD step; issued as soon as the bucket's last wgrad is done" % args.bucket_mb)
+                       "sync": ("NCCL all-reduce(avg) of the flat gradient buffer in buckets of >= %.0f MB cut at layer boundaries, on "
+                                "its own stream as soon as a bucket's last wgrad is done, each followed by that bucket's SGD step on the "
+                                "optimizer stream; NCCL width %s CTAs = SMs the conv grids leave free meanwhile"
+                                % (args.bucket_mb, os.environ.get("CONVNET_B200_NCCL_CTAS", "16" if world <= 4 else "24")))
                                if world > 1 else "single GPU",
                        "train_gflop_per_image": net.flops_train / args.batch / 1e9,
                        "baseline_config3_256_per_gpu": cfg3},

@@ -131,7 +131,7 @@ class Net:
             out["buckets"].append({"MB": round(mb, 3), "exchange_begin_ms": c0, "exchange_end_ms": c1, "sgd_end_ms": s1})
         return out
 
-    def dp_init(self, rank, world, id_bytes, bucket_floats=8 << 20):
+    def dp_init(self, rank, world, id_bytes, bucket_floats=32 << 20):
         assert len(id_bytes) == 128
         rc = self.H.cnb_net_dp_init(self.h, rank, world, bytes(id_bytes), bucket_floats)
         if rc != 0:
