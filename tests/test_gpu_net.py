@@ -85,6 +85,30 @@ def test_alexnet_step_small_batch(env, mode):
     n.close()
 
 
+def test_traced_step_reports_an_ordered_timeline(env):
+    """ConvNet::TraceStep (cnb_net_trace_step): one real training step with timing events — milestones in order, one SGD end
+    per bucket, no exchange window on a single rank — and the step it ran is a normal step (parameters moved)."""
+    torch, lib, net = env
+    lib.set_precision("bf16")
+    n = net.Net("alexnet", 128, seed=1)
+    g = torch.Generator(device="cuda").manual_seed(0)
+    n.input_tensor().normal_(generator=g)
+    n.labels_tensor().copy_(torch.randint(0, 1000, (128,), device="cuda", generator=g, dtype=torch.int32))
+    n.train_step(False)
+    p0 = n.params_tensor().clone()
+    t = n.trace_step()
+    assert 0 < t["fprop_end_ms"] < t["bprop_compute_end_ms"] <= t["step_end_ms"] < 100
+    assert len(t["buckets"]) >= 2 and abs(sum(b["MB"] for b in t["buckets"]) - 4 * 104321024 / 1e6) < 1.0
+    for b in t["buckets"]:
+        assert b["exchange_begin_ms"] == -1 and b["exchange_end_ms"] == -1
+        assert t["fprop_end_ms"] < b["sgd_end_ms"] <= t["step_end_ms"] + 1e-3
+    assert not torch.equal(p0, n.params_tensor())
+    l = n.train_step(True)                                       # and the ordinary step still works afterwards
+    assert math.isfinite(l)
+    n.close()
+    lib.set_precision("tf32")
+
+
 def test_c3d_video_net_step(env):
     torch, lib, net = env
     lib.set_precision("tf32")
