@@ -462,9 +462,10 @@ __global__ void __launch_bounds__(256) pool_undo_masked_kernel(PoolGeom g, const
 
 // The same undo for stride 2, windows up to 3 x 3, organised by PATCHES: the 2 x 2 input elements whose offset from the
 // padded origin is (2*mx + a, 2*my + b) are covered by the same 2 x 2 windows {mx-1, mx} x {my-1, my}, so one thread loads
-// those four (gradient, mask) pairs once and writes four outputs — a quarter of the L2 requests of the per-element kernel
-// above, which is what bounded it (13 TB/s of L2 reads for 3 TB/s of DRAM traffic on pool1).  Sums run over the windows in
-// the same ascending (y, x) order as the per-element kernels: results are bit-identical to them.
+// those four (gradient, mask) pairs once and writes four outputs.  The per-element kernel above is bound by instruction
+// issue (75 % of cycles, DRAM at 2.8 TB/s: profiles/r2_membound_kernels.md) — every element loads, unpacks and tests its
+// covering windows again; here that work is shared by the patch: 1.46x fewer instructions, 1.46x faster on pool1.  Sums run
+// over the windows in the same ascending (y, x) order as the per-element kernels: results are bit-identical to them.
 template <int VEC>
 __global__ void __launch_bounds__(256) pool_undo_masked_patch_kernel(PoolGeom g, const float* __restrict__ grads,
                                                                      const uint16_t* __restrict__ tie_masks, float* targets,
