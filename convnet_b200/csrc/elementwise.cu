@@ -244,6 +244,44 @@ void dropout_apply(float* x, long long n, float dropprob, float scale, unsigned 
   dropout_kernel<<<blocks_for(std::max(n4, n - 4 * n4), 256), 256, 0, state().stream>>>(x, nullptr, n, n4, dropprob, scale, seed, out16);
   count_launch(); CNB_LAUNCH_CHECK("dropout_apply");
 }
+
+// crop + mirror + transpose of a minibatch out of an image-major chunk (convnet_b200_extract_patches).  A 32 x 32 tile of
+// (image, patch column) for one (patch row, colour) goes through shared memory: the reads run along a source row (128
+// contiguous bytes per image, reversed when mirrored), the writes along the images (the fastest axis of the layer state).
+// The reference's kernel maps threads to patch columns and so stores with a stride of N floats (cudamat_kernels.cu:1655).
+__global__ void __launch_bounds__(256) extract_patches_kernel(const float* __restrict__ images, float* __restrict__ patches,
+                                                              const float* __restrict__ width_offset,
+                                                              const float* __restrict__ height_offset,
+                                                              const float* __restrict__ flip, int N, int W, int H, int pw, int ph,
+                                                              int C) {
+  __shared__ float tile[32][33];
+  const int row = (int)(blockIdx.z % (unsigned)ph), color = (int)(blockIdx.z / (unsigned)ph);
+  const int n0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int n = n0 + k, dc = c0 + (int)threadIdx.x;
+    if (n < N && dc < pw) {
+      int sr = (int)height_offset[n] + row, sc = (int)width_offset[n] + dc;
+      if (flip[n] > 0.5f) sc = W - sc - 1;
+      sr = min(max(sr, 0), H - 1); sc = min(max(sc, 0), W - 1);
+      tile[k][threadIdx.x] = __ldg(images + sc + (size_t)W * (sr + (size_t)H * (color + (size_t)C * n)));
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.y; k < 32; k += 8) {
+    const int dc = c0 + k, n = n0 + (int)threadIdx.x;
+    if (n < N && dc < pw) patches[n + (size_t)N * (dc + (size_t)pw * (row + (size_t)ph * color))] = tile[threadIdx.x][k];
+  }
+}
+int extract_patches(const float* images, float* patches, const float* width_offset, const float* height_offset,
+                    const float* flip, int N, int W, int H, int pw, int ph, int C) {
+  if (N <= 0 || pw <= 0 || ph <= 0 || C <= 0) return 0;
+  if ((long long)ph * C > 65535 || ceil_div(N, 32) > 65535) return -1;
+  bf16_note_write(patches, (long long)N * pw * ph * C);
+  const dim3 grid((unsigned)ceil_div(pw, 32), (unsigned)ceil_div(N, 32), (unsigned)(ph * C));
+  extract_patches_kernel<<<grid, dim3(32, 8), 0, state().stream>>>(images, patches, width_offset, height_offset, flip, N, W, H, pw, ph, C);
+  count_launch();
+  return cudaGetLastError() == cudaSuccess ? 0 : -3;
+}
 }  // namespace cnb
 
 using namespace cnb;

@@ -85,6 +85,20 @@ void convnet_b200_fuse_next_bias_grad(float* grad_bias, float scaleTargets, floa
 void convnet_b200_fuse_next_scale(float scale) { state().fuse.out_scale = scale; }
 void convnet_b200_pool_cache_next(void) { state().fuse.pool_cache = 1; }
 void convnet_b200_prestage_next(void) { state().fuse.prestage = 1; }
+int convnet_b200_extract_patches(cudamat* images, cudamat* patches, cudamat* width_offset, cudamat* height_offset,
+                                 cudamat* flip, int img_width, int img_height, int patch_width, int patch_height) {
+  // argument checks of cudamat.cu:2699-2713
+  if (img_width <= 0 || img_height <= 0 || patch_width <= 0 || patch_height <= 0) return -1;
+  const int num_images = images->size[1];
+  const int num_colors = images->size[0] / (img_width * img_height);
+  if (num_colors <= 0 || images->size[0] != num_colors * img_width * img_height) return -1;
+  if (patches->size[1] != num_colors * patch_width * patch_height || patches->size[0] != num_images) return -1;
+  if (width_offset->size[0] * width_offset->size[1] != num_images) return -1;
+  if (height_offset->size[0] * height_offset->size[1] != num_images) return -1;
+  if (flip->size[0] * flip->size[1] != num_images) return -1;
+  return extract_patches(images->data_device, patches->data_device, width_offset->data_device, height_offset->data_device,
+                         flip->data_device, num_images, img_width, img_height, patch_width, patch_height, num_colors);
+}
 void convnet_b200_fuse_next_dropout(float dropprob, float scale, unsigned long long seed) {
   Fuse& f = state().fuse;
   f.drop_prob = dropprob; f.drop_scale = scale; f.drop_seed = seed;

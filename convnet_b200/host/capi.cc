@@ -2,6 +2,7 @@
 #include <cstring>
 
 #include "convnet.h"
+#include "data.h"
 
 using namespace cnbhost;
 
@@ -101,5 +102,31 @@ API int cnb_model_edge_params(const char* model, int batch, int cap, long long* 
   ConvNet net(m, batch);
   int n = 0;
   for (Edge* e : net.Edges()) { if (n >= cap) break; sizes[n++] = (long long)e->GetParameterMemoryRequirement(); }
+  return n;
+}
+
+// ---- the device side of the input pipeline (data.h): a GPU-resident chunk + per-minibatch crop / mirror into the net's input
+API void* cnb_data_create(int chunk_size, int channels, int image_size_y, int image_size_x, int gpu_image_size_y,
+                          int gpu_image_size_x, int translate, int flip, unsigned long long seed) {
+  return new DataIterator(chunk_size, channels, image_size_y, image_size_x, gpu_image_size_y, gpu_image_size_x,
+                          translate != 0, flip != 0, seed);
+}
+API void cnb_data_destroy(void* d) { delete (DataIterator*)d; }
+API void cnb_data_upload(void* d, const float* host, int first, int count) { ((DataIterator*)d)->Upload(host, first, count); }
+// DataHandler::GetBatch for the input layer of `net`: sample the jitter, then cut images [start, start + batch) into it
+API void cnb_data_get_batch(void* d, void* net, int start, int multiplicity_id) {
+  DataIterator* it = (DataIterator*)d;
+  Matrix& dest = ((NetHandle*)net)->net->InputLayer().GetState();
+  it->SampleNoise(dest.GetRows(), multiplicity_id);
+  it->AddNoise(start, dest);
+}
+// the jitter of the last minibatch (host copies): out = {width offsets, height offsets, mirror bits}, 3 x batch floats
+API int cnb_data_last_noise(void* d, float* out, int cap) {
+  DataIterator* it = (DataIterator*)d;
+  const int n = (int)it->LastWidthOffsets().size();
+  if (cap < 3 * n) return -1;
+  memcpy(out, it->LastWidthOffsets().data(), sizeof(float) * n);
+  memcpy(out + n, it->LastHeightOffsets().data(), sizeof(float) * n);
+  memcpy(out + 2 * n, it->LastFlipBits().data(), sizeof(float) * n);
   return n;
 }

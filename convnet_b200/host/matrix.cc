@@ -104,6 +104,12 @@ void Matrix::ConvDown(Matrix& deriv_output, Matrix& w, Matrix& deriv_input, Conv
   convDownGemm(deriv_output.GetMat(), w.GetMat(), deriv_input.GetMat(), &deriv_output.GetShape4D(), &w.GetShape4D(),
                &deriv_input.GetShape4D(), conv_desc, scale_targets);
 }
+void Matrix::ExtractPatches(Matrix& source, Matrix& dest, Matrix& width_offset, Matrix& height_offset, Matrix& flip_bit,
+                            int image_size_y, int image_size_x, int patch_size_y, int patch_size_x) {   // src/matrix.cc:1030-1042
+  const int err_code = convnet_b200_extract_patches(source.GetMat(), dest.GetMat(), width_offset.GetMat(), height_offset.GetMat(),
+                                                    flip_bit.GetMat(), image_size_x, image_size_y, patch_size_x, patch_size_y);
+  if (err_code != 0) { fprintf(stderr, "Error extracting patches (%d)\n", err_code); exit(1); }
+}
 void Matrix::ConvOutp(Matrix& input, Matrix& deriv_output, Matrix& dw, ConvDesc conv_desc, int, int,
                       float scale_targets, float scale_outputs) {
   convOutpGemm(input.GetMat(), deriv_output.GetMat(), dw.GetMat(), &input.GetShape4D(), &deriv_output.GetShape4D(),

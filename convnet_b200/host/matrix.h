@@ -75,6 +75,10 @@ class Matrix {
                                              int numFilters, int sizeF, float addScale, float powScale, bool blocked,
                                              int image_size_t);
 
+  // minibatch crop / mirror / transpose out of an image-major chunk (src/matrix.cc:1030-1042 -> extract_patches)
+  static void ExtractPatches(Matrix& source, Matrix& dest, Matrix& width_offset, Matrix& height_offset, Matrix& flip_bit,
+                             int image_size_y, int image_size_x, int patch_size_y, int patch_size_x);
+
   static void SetupCUDADevice(int board);                     // src/matrix.cc:528
   static cudaStream_t Stream();
 

@@ -30,6 +30,9 @@ def load_host():
             "cnb_net_fprop": ([vp, i], None), "cnb_net_bprop": ([vp], None), "cnb_net_update": ([vp], None),
             "cnb_net_loss": ([vp], f), "cnb_net_train_step": ([vp, ct.POINTER(f)], None),
             "cnb_net_trace_step": ([vp, ct.POINTER(f), i], i),
+            "cnb_data_create": ([i, i, i, i, i, i, i, i, ct.c_ulonglong], vp), "cnb_data_destroy": ([vp], None),
+            "cnb_data_upload": ([vp, vp, i, i], None), "cnb_data_get_batch": ([vp, vp, i, i], None),
+            "cnb_data_last_noise": ([vp, ct.POINTER(f), i], i),
             "cnb_dp_unique_id": ([ct.c_char_p], i), "cnb_net_dp_init": ([vp, i, i, ct.c_char_p, ll], i),
             "cnb_plan_buckets": ([i, ct.POINTER(ll), ct.POINTER(ll), ll, i, ct.POINTER(ll), ct.POINTER(ll), ct.POINTER(i)], i),
             "cnb_model_edge_params": ([ct.c_char_p, i, i, ct.POINTER(ll)], i),
@@ -175,3 +178,38 @@ def dp_unique_id():
     if load_host().cnb_dp_unique_id(buf) != 0:
         raise RuntimeError("ncclGetUniqueId failed")
     return buf.raw
+
+
+class DataIterator:
+    """Device side of the reference's input pipeline (host/data.h; src/datahandler.cc:146-200, 520-568): a chunk of images
+    resident on the GPU, and per minibatch a random (or centre / corner) crop + mirror into the net's input layer."""
+
+    def __init__(self, chunk_size, channels, image_size, gpu_image_size, translate=True, flip=True, seed=1):
+        self.H = load_host()
+        isy, isx = (image_size, image_size) if isinstance(image_size, int) else image_size
+        gy, gx = (gpu_image_size, gpu_image_size) if isinstance(gpu_image_size, int) else gpu_image_size
+        self.chunk_size, self.dims = chunk_size, channels * isy * isx
+        self.h = self.H.cnb_data_create(chunk_size, channels, isy, isx, gy, gx, int(translate), int(flip), seed)
+
+    def close(self):
+        if self.h:
+            self.H.cnb_data_destroy(self.h)
+            self.h = None
+
+    def upload(self, host_tensor, first=0):
+        """host_tensor: float32 CPU tensor [count, channels, rows, cols] (pinned for an asynchronous copy)"""
+        import torch
+        t = host_tensor.contiguous()
+        assert t.dtype == torch.float32 and t.device.type == "cpu" and t[0].numel() == self.dims
+        self.H.cnb_data_upload(self.h, t.data_ptr(), first, t.shape[0])
+        self._keep = t                                   # the copy is asynchronous
+
+    def get_batch(self, net, start=0, multiplicity_id=0):
+        self.H.cnb_data_get_batch(self.h, net.h, start, multiplicity_id)
+
+    def last_noise(self, batch):
+        buf = (ct.c_float * (3 * batch))()
+        n = self.H.cnb_data_last_noise(self.h, buf, 3 * batch)
+        assert n == batch
+        v = [buf[k] for k in range(3 * batch)]
+        return v[:batch], v[batch:2 * batch], v[2 * batch:]

@@ -164,6 +164,22 @@ typedef struct CnbSgdTensor {
 } CnbSgdTensor;
 void cnb_sgd_momentum_multi(const CnbSgdTensor* tensors, int count);
 
+/* ---- input pipeline, device side -------------------------------------------------------------------
+ * The reference keeps a chunk of the data set on the GPU, one image per COLUMN (pixel index = col + W*(row + H*color)),
+ * and cuts every minibatch out of it with a random crop and mirror per image while transposing it into the image-fastest
+ * layout of the input layer: DataIterator::AddNoise -> Matrix::ExtractPatches (src/datahandler.cc:520-531,
+ * src/matrix.cc:1030-1042) -> extract_patches (cudamat/cudamat.cuh:265, cudamat.cu:2699-2742, kernel
+ * cudamat_kernels.cu:1655-1669).  Same arguments, same element-for-element result, same error codes
+ * (ERROR_INCOMPATIBLE_DIMENSIONS = -1, CUDA_ERROR = -3); exported under its own name because the reference's copy lives in
+ * libcudamat.so, which a drop-in build keeps linking:
+ *   patches[n + N*(x + pw*(y + ph*c))] = images[sx + W*(height_offset[n] + y + H*(c + C*n))],
+ *   sx = width_offset[n] + x, mirrored to W - 1 - sx when flip[n] > 0.5.
+ * `images` is (C*W*H) x N in cudamat's size[] convention (size[1] = N images), `patches` is N x (C*pw*ph); the three
+ * per-image vectors hold N floats on the device.  Source coordinates are clamped to the image (the reference reads out of
+ * bounds for a crop that does not fit).  Runs on the library's stream. */
+int convnet_b200_extract_patches(cudamat* images, cudamat* patches, cudamat* width_offset, cudamat* height_offset,
+                                 cudamat* flip, int img_width, int img_height, int patch_width, int patch_height);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -393,3 +393,23 @@ void oracle_rnormUndo(const float* deriv, const float* data, float* target, long
   }
   free(denoms);
 }
+
+/* ---- input pipeline: minibatch crop / mirror (eigenmat/eigenmat.cc:2046-2090) ---------------------------------------- */
+int oracle_extract_patches(const float* images, float* patches, const float* width_offset, const float* height_offset,
+                           const float* flip, int num_images, int num_colors, int img_width, int img_height,
+                           int patch_width, int patch_height) {
+  for (long n = 0; n < num_images; n++) {
+    const int x0 = (int)width_offset[n], y0 = (int)height_offset[n];
+    const int mirror = flip[n] > 0.5f;
+    for (long c = 0; c < num_colors; c++)
+      for (long y = 0; y < patch_height; y++)
+        for (long x = 0; x < patch_width; x++) {
+          long sx = x0 + x;
+          if (mirror) sx = img_width - sx - 1;
+          const long sy = y0 + y;
+          patches[n + num_images * (x + patch_width * (y + patch_height * c))] =
+              images[sx + img_width * (sy + img_height * (c + num_colors * n))];
+        }
+  }
+  return 0;
+}

@@ -82,6 +82,13 @@ void oracle_rnormUndo(const float* outGrads, const float* inputs, float* targets
                       long num_els, int numFilters, int sizeF, float addScale,
                       float powScale, int blocked);
 
+/* crop + mirror + transpose of a minibatch out of an image-major chunk; follows eigenmat/eigenmat.cc:2046-2090
+ * (= cudamat/cudamat_kernels.cu:1655-1669).  images: one image per column, pixel = col + W*(row + H*color);
+ * patches: image fastest, n + N*(x + pw*(y + ph*c)).  Returns 0. */
+int oracle_extract_patches(const float* images, float* patches, const float* width_offset, const float* height_offset,
+                           const float* flip, int num_images, int num_colors, int img_width, int img_height,
+                           int patch_width, int patch_height);
+
 #ifdef __cplusplus
 }
 #endif

@@ -7,6 +7,7 @@
  * (eigenmat/cpumat_conv.h:6-22) through plain pointers.
  */
 #include "cpumat_conv.h"   // -I/root/reference/eigenmat at build time
+#include "eigenmat.h"      // extract_patches (eigenmat.cc:2046)
 
 #include <cstdlib>
 #include <new>
@@ -67,6 +68,15 @@ void ref_rnormUndo(float* outGrads, float* inputs, float* targets, int rows, int
                    int numFilters, int sizeF, float addScale, float powScale, int blocked) {
   eigenmat G = wrap(outGrads, rows, cols), A = wrap(inputs, rows, cols), C = wrap(targets, rows, cols);
   ResponseNormCrossMapUndo(&G, &A, &C, numFilters, sizeF, addScale, powScale, blocked != 0);
+}
+
+// the reference's CPU crop / mirror of a minibatch (eigenmat/eigenmat.cc:2046-2090); images: (C*W*H) x N, patches: N x (C*pw*ph)
+int ref_extract_patches(float* images, float* patches, float* width_offset, float* height_offset, float* flip,
+                        int num_images, int num_colors, int img_width, int img_height, int patch_width, int patch_height) {
+  eigenmat I = wrap(images, num_colors * img_width * img_height, num_images),
+           P = wrap(patches, num_images, num_colors * patch_width * patch_height),
+           X = wrap(width_offset, 1, num_images), Y = wrap(height_offset, 1, num_images), F = wrap(flip, 1, num_images);
+  return extract_patches(&I, &P, &X, &Y, &F, img_width, img_height, patch_width, patch_height);
 }
 
 }  // extern "C"

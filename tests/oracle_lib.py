@@ -68,6 +68,8 @@ class Oracle:
         L.oracle_rnorm.argtypes = [FP, FP, ct.c_long, ct.c_int, ct.c_int, ct.c_float, ct.c_float, ct.c_int]
         L.oracle_rnormUndo.argtypes = [FP, FP, FP, ct.c_long, ct.c_int, ct.c_int, ct.c_float,
                                        ct.c_float, ct.c_int]
+        L.oracle_extract_patches.argtypes = [FP, FP, FP, FP, FP] + [ct.c_int] * 6
+        L.oracle_extract_patches.restype = ct.c_int
 
     # --- conv (2-D) ---
     def convUp(self, images, filters, targets, ish, fsh, tsh, d, scaleTargets=0.0, scaleOutput=1.0, conv=True):
@@ -109,6 +111,12 @@ class Oracle:
     def avgPoolUndo(self, avgGrads, targets, gsh, tsh, d, scaleTargets=0.0, scaleOutput=1.0):
         self.lib.oracle_avgPoolUndo(_p(avgGrads), _p(targets), s4(gsh), s4(tsh), d, scaleTargets, scaleOutput)
 
+    # --- input pipeline ---
+    def extract_patches(self, images, patches, width_offset, height_offset, flip, N, C, W, H, pw, ph):
+        """images: flat float32, image n at [n*C*H*W, (n+1)*C*H*W) as (c, y, x); patches: flat, image fastest"""
+        return self.lib.oracle_extract_patches(_p(images), _p(patches), _p(width_offset), _p(height_offset), _p(flip),
+                                               N, C, W, H, pw, ph)
+
     # --- response norm ---
     def rnorm(self, images, targets, numFilters, sizeF, addScale, powScale, blocked=False):
         self.lib.oracle_rnorm(_p(images), _p(targets), images.size, numFilters, sizeF, addScale, powScale,
@@ -138,6 +146,9 @@ class RefLib:
         L.ref_rnorm.argtypes = [FP, FP, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_float, ct.c_float, ct.c_int]
         L.ref_rnormUndo.argtypes = [FP, FP, FP, ct.c_int, ct.c_int, ct.c_int, ct.c_int, ct.c_float, ct.c_float,
                                     ct.c_int]
+        if hasattr(L, "ref_extract_patches"):                 # a prebuilt _ref from before this door existed lacks it
+            L.ref_extract_patches.argtypes = [FP, FP, FP, FP, FP] + [ct.c_int] * 6
+            L.ref_extract_patches.restype = ct.c_int
 
     def _s(self, t):
         return (ct.c_int * 4)(*[int(v) for v in t])
@@ -153,6 +164,10 @@ class RefLib:
     def convOutp(self, images, derivs, targets, ish, dsh, tsh, d, scaleTargets=0.0, scaleOutput=1.0, conv=True):
         self.lib.ref_convOutp(_p(images), _p(derivs), _p(targets), self._s(ish), self._s(dsh), self._s(tsh), d,
                               scaleTargets, scaleOutput, int(conv))
+
+    def extract_patches(self, images, patches, width_offset, height_offset, flip, N, C, W, H, pw, ph):
+        return self.lib.ref_extract_patches(_p(images), _p(patches), _p(width_offset), _p(height_offset), _p(flip),
+                                            N, C, W, H, pw, ph)
 
     def rnorm(self, images, targets, numFilters, sizeF, addScale, powScale, blocked=False):
         self.lib.ref_rnorm(_p(images), _p(targets), images.shape[0], images.shape[1], numFilters, sizeF,
