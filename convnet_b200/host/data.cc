@@ -23,7 +23,12 @@ DataIterator::DataIterator(int chunk_size, int channels, int image_size_y, int i
   }
   data_.AllocateGPUMemory(NumDims(), chunk_size);          // one image per column (src/datahandler.cc:60-75)
 }
-DataIterator::~DataIterator() { if (pinned_) cudaFreeHost(pinned_); }
+DataIterator::~DataIterator() {
+  if (pinned_) {
+    cudaStreamSynchronize(Matrix::Stream());                 // the last minibatch's offset copies may still read the block
+    cudaFreeHost(pinned_);
+  }
+}
 
 uint64_t DataIterator::NextRand() {                         // splitmix64
   uint64_t z = (rng_ += 0x9E3779B97F4A7C15ULL);

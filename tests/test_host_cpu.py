@@ -55,6 +55,16 @@ def test_bucket_plan_partitions_the_flat_buffer(host, model, bucket):
         assert len(plan) == sum(1 for s in sizes if s > 0)
 
 
+def test_default_bucket_plan_of_the_bench(host):
+    """bench.py's default (--bucket-mb 128) on AlexNet: three exchanges per step — {fc8, fc7, fc6} as soon as fc6's
+    gradient exists, {conv5 ... conv2}, and conv1 alone (profiles/r2_scaling_timeline.md)."""
+    sizes = host.model_edge_params("alexnet")
+    plan, total = host.plan_buckets(sizes, int(128 * (1 << 20) / 4))
+    assert [trig for _, _, trig in plan] == [16, 3, 0]         # lowest edge of each bucket: fc6, conv2, conv1
+    mb = [round((hi - lo) * 4 / 1e6, 1) for lo, hi, _ in plan]
+    assert mb == [385.5, 31.7, 0.1] and total == 104321024
+
+
 WORKER = r'''
 import os, sys, numpy as np, torch, torch.distributed as dist
 sys.path.insert(0, sys.argv[1])
