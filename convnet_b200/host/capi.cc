@@ -130,3 +130,7 @@ API int cnb_data_last_noise(void* d, float* out, int cap) {
   memcpy(out + 2 * n, it->LastFlipBits().data(), sizeof(float) * n);
   return n;
 }
+// pure host logic (no GPU): offset of deterministic view `multiplicity_id` for a free range of (max_x, max_y) pixels
+API void cnb_data_view_offset(int multiplicity_id, int max_offset_x, int max_offset_y, int* w, int* h) {
+  DataIterator::ViewOffset(multiplicity_id, max_offset_x, max_offset_y, w, h);
+}

@@ -43,6 +43,15 @@ void DataIterator::Upload(const float* host, int first, int count) {
                                   cudaMemcpyHostToDevice, Matrix::Stream()));
 }
 
+void DataIterator::ViewOffset(int multiplicity_id, int max_offset_x, int max_offset_y, int* w, int* h) {
+  // position of view k = multiplicity_id % 5 along (x, y), in halves of the free range: 1 = centred, 0 / 2 = the two ends
+  static const int kView[5][2] = {{1, 1}, {0, 0}, {2, 0}, {2, 2}, {0, 2}};
+  auto place = [](int half_steps, int max_offset) { return half_steps == 1 ? max_offset / 2 : (half_steps == 2 ? max_offset : 0); };
+  const int view = multiplicity_id % 5;
+  *w = place(kView[view][0], max_offset_x);
+  *h = place(kView[view][1], max_offset_y);
+}
+
 void DataIterator::SampleNoise(int batch_size, int multiplicity_id) {
   const int max_offset_y = image_size_y_ - gpu_image_size_y_, max_offset_x = image_size_x_ - gpu_image_size_x_;
   if (width_offset_.GetCols() != batch_size || width_offset_.GetDevData() == nullptr) {
@@ -56,16 +65,11 @@ void DataIterator::SampleNoise(int batch_size, int multiplicity_id) {
       h_ho_[i] = (float)(int)(Uniform() * (max_offset_y + 1));
       h_wo_[i] = (float)(int)(Uniform() * (max_offset_x + 1));
     }
-  } else {                                                   // centre or corner patch
-    int w = 0, h = 0;
-    switch (multiplicity_id % 5) {
-      case 0: w = max_offset_x / 2; h = max_offset_y / 2; break;
-      case 1: w = 0; h = 0; break;
-      case 2: w = max_offset_x; h = 0; break;
-      case 3: w = max_offset_x; h = max_offset_y; break;
-      case 4: w = 0; h = max_offset_y; break;
-    }
-    for (int i = 0; i < batch_size; i++) { h_wo_[i] = (float)w; h_ho_[i] = (float)h; }
+  } else {                                                   // deterministic views: the centre, then the four corners
+    int wi, hi;
+    ViewOffset(multiplicity_id, max_offset_x, max_offset_y, &wi, &hi);
+    const float w = (float)wi, h = (float)hi;
+    for (int i = 0; i < batch_size; i++) { h_wo_[i] = w; h_ho_[i] = h; }
   }
   for (int i = 0; i < batch_size; i++) h_flip_[i] = flip_ ? Uniform() : (float)(multiplicity_id / 5);   // mirrored if > 0.5
   // one pinned staging block: the three vectors travel behind whatever the stream is doing

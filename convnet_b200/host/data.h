@@ -24,6 +24,8 @@ class DataIterator {
   // :533-568 — the jitter of one minibatch: random offsets when `translate`, else the centre / corner crop number
   // multiplicity_id % 5; random mirror bits when `flip`, else multiplicity_id / 5
   void SampleNoise(int batch_size, int multiplicity_id);
+  // the deterministic (translate == false) views of :547-556: centre, top-left, top-right, bottom-right, bottom-left
+  static void ViewOffset(int multiplicity_id, int max_offset_x, int max_offset_y, int* w, int* h);
   // :520-531 + GetBatch's slice: images [start, start + batch) of the chunk -> dest (batch x C*gy*gx, image fastest)
   void AddNoise(int start, Matrix& dest);
   const std::vector<float>& LastWidthOffsets() const { return h_wo_; }

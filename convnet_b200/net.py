@@ -33,6 +33,7 @@ def load_host():
             "cnb_data_create": ([i, i, i, i, i, i, i, i, ct.c_ulonglong], vp), "cnb_data_destroy": ([vp], None),
             "cnb_data_upload": ([vp, vp, i, i], None), "cnb_data_get_batch": ([vp, vp, i, i], None),
             "cnb_data_last_noise": ([vp, ct.POINTER(f), i], i),
+            "cnb_data_view_offset": ([i, i, i, ct.POINTER(i), ct.POINTER(i)], None),
             "cnb_dp_unique_id": ([ct.c_char_p], i), "cnb_net_dp_init": ([vp, i, i, ct.c_char_p, ll], i),
             "cnb_plan_buckets": ([i, ct.POINTER(ll), ct.POINTER(ll), ll, i, ct.POINTER(ll), ct.POINTER(ll), ct.POINTER(i)], i),
             "cnb_model_edge_params": ([ct.c_char_p, i, i, ct.POINTER(ll)], i),
@@ -213,3 +214,11 @@ class DataIterator:
         assert n == batch
         v = [buf[k] for k in range(3 * batch)]
         return v[:batch], v[batch:2 * batch], v[2 * batch:]
+
+
+def view_offset(multiplicity_id, max_offset_x, max_offset_y):
+    """(w, h) of the deterministic crop number multiplicity_id (host logic only, no GPU)"""
+    H = load_host()
+    w, h = ct.c_int(0), ct.c_int(0)
+    H.cnb_data_view_offset(multiplicity_id, max_offset_x, max_offset_y, ct.byref(w), ct.byref(h))
+    return w.value, h.value

@@ -69,6 +69,16 @@ def test_argument_checks_return_the_reference_error_code():
     assert L.convnet_b200_extract_patches(m(C * W * H + 1, N), m(N, C * pw * ph), vec, vec, vec, W, H, pw, ph) == -1
 
 
+def test_deterministic_views_follow_the_reference_rule():
+    """src/datahandler.cc:547-556: view k % 5 = centre, top-left, top-right, bottom-right, bottom-left (host logic, CPU)"""
+    from convnet_b200 import build, net
+    build.build_host(); net.load_host()
+    for mx, my in ((32, 32), (5, 9), (0, 0), (1, 7)):
+        want = [(mx // 2, my // 2), (0, 0), (mx, 0), (mx, my), (0, my)]
+        for k in range(12):
+            assert net.view_offset(k, mx, my) == want[k % 5]
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("case", CASES + [(128, 3, 256, 256, 224, 224), (100, 1, 28, 28, 28, 28), (130, 3, 70, 50, 65, 33)])
 def test_kernel_equals_the_oracle(case):
