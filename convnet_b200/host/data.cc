@@ -62,8 +62,9 @@ void DataIterator::SampleNoise(int batch_size, int multiplicity_id) {
   h_wo_.assign(batch_size, 0.f); h_ho_.assign(batch_size, 0.f); h_flip_.assign(batch_size, 0.f);
   if (translate_) {                                          // random jitter: uniform * (max + 1), rounded down
     for (int i = 0; i < batch_size; i++) {
-      h_ho_[i] = (float)(int)(Uniform() * (max_offset_y + 1));
-      h_wo_[i] = (float)(int)(Uniform() * (max_offset_x + 1));
+      const int oy = (int)(Uniform() * (max_offset_y + 1)), ox = (int)(Uniform() * (max_offset_x + 1));
+      h_ho_[i] = (float)(oy > max_offset_y ? max_offset_y : oy);      // (the product can round up to max + 1 in fp32)
+      h_wo_[i] = (float)(ox > max_offset_x ? max_offset_x : ox);
     }
   } else {                                                   // deterministic views: the centre, then the four corners
     int wi, hi;
